@@ -1,0 +1,187 @@
+"""Pins the oracle against the LIVE reference and writes tests/golden/*.pt.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):   python -m oracle.make_golden
+The reference is imported unmodified through an import shim (stubs for the four
+training-only dependencies that are not installed here; T5Config.from_pretrained
+patched so that no network is touched) -- SURVEY.md section 8c.
+
+What is checked at generation time (hard asserts):
+  * oracle.unet_ref.unet_forward == reference Unet.forward (cond and null branch)
+  * oracle.sampler_ref.imagen_sample == reference Imagen.sample on the same seed
+  * oracle.sampler_ref.elucidated_sample == reference ElucidatedImagen.sample
+  * cascade (lowres_cond SR unet, memory_efficient) variants of the above
+What is written: small fixtures (weights of tiny U-Nets + inputs + reference
+outputs) that the CPU and GPU test-suites replay without the reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+import importlib.machinery
+
+import torch
+
+
+def _install_shim():
+    import transformers  # noqa: F401  (must be imported before the stubs)
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class _Any:
+        def __init__(self, *a, **k):
+            pass
+
+    k = stub('kornia')
+    k.augmentation = stub('kornia.augmentation', RandomCrop=_Any)
+    stub('accelerate', Accelerator=_Any, DistributedType=_Any, DistributedDataParallelKwargs=_Any)
+    stub('ema_pytorch', EMA=_Any)
+    stub('pytorch_warmup', LinearWarmup=_Any)
+    from transformers import T5Config
+    T5Config.from_pretrained = classmethod(
+        lambda cls, name, *a, **kw: T5Config(d_model=1024 if 'large' in name else 768))
+    sys.path.insert(0, '/root/reference')
+
+
+def _maxdiff(a, b):
+    return (a - b).abs().max().item()
+
+
+def main():
+    _install_shim()
+    import imagen_pytorch as ref
+    from oracle import unet_ref, sampler_ref
+
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(8)
+
+    # ---------------------------------------------------------------- 1. base unet forward (cfg-1 shape family)
+    shapes_out = {}
+
+    def build(name, kwargs, seed, lowres=False):
+        u = ref.Unet(**kwargs, lowres_cond=lowres)
+        shapes = {k: tuple(v.shape) for k, v in u.state_dict().items()}
+        shapes_out[name] = shapes
+        sd = unet_ref.synth_state_dict(shapes, seed=seed)
+        u.load_state_dict(sd)                       # strict: every key, every shape
+        u.eval()
+        cfg = unet_ref.unet_config(**kwargs, lowres_cond=lowres)
+        return u, sd, cfg
+
+    base_kw = dict(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24)
+    u, sd, cfg = build('base', base_kw, 0)
+    g = torch.Generator().manual_seed(7)
+    B = 2
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([-1.7, 0.6])
+    te = torch.randn(B, 24, 64, generator=g)
+    te[1, 17:] = 0.                                   # ragged text -> mask has False entries
+    tm = torch.any(te != 0., dim=-1)
+    with torch.no_grad():
+        r_c = u(x, t, text_embeds=te, text_mask=tm)
+        r_n = u(x, t, text_embeds=te, text_mask=tm, cond_drop_prob=1.)
+        r_g = u.forward_with_cond_scale(x, t, text_embeds=te, text_mask=tm, cond_scale=3.)
+        o_c = unet_ref.unet_forward(sd, cfg, x, t, text_embeds=te, text_mask=tm)
+        o_n = unet_ref.unet_forward(sd, cfg, x, t, text_embeds=te, text_mask=tm, cond_drop_prob=1.)
+        o_g = unet_ref.unet_forward_with_cond_scale(sd, cfg, x, t, text_embeds=te, text_mask=tm, cond_scale=3.)
+    for name, a, b in (('cond', r_c, o_c), ('null', r_n, o_n), ('cfg', r_g, o_g)):
+        d = _maxdiff(a, b)
+        print(f'[unet base {name}] ref-vs-oracle max|d| = {d:.3e}  (|ref|max {a.abs().max():.3f})')
+        assert d < 1e-5 * max(1., a.abs().max().item()), name   # fp32 re-association only
+    torch.save(dict(kwargs=base_kw, wseed=0, x=x, t=t, text_embeds=te, text_mask=tm,
+                    out_cond=r_c, out_null=r_n, out_cfg3=r_g), os.path.join(out_dir, 'unet_base_dim32.pt'))
+
+    # ---------------------------------------------------------------- 2. SR unet forward (lowres_cond, memory_efficient, mixed attns)
+    sr_kw = dict(dim=32, dim_mults=(1, 2, 4), text_embed_dim=64, max_text_len=24, num_resnet_blocks=(1, 2, 2),
+                 layer_attns=(False, False, True), layer_cross_attns=(False, False, True), memory_efficient=True)
+    us, sds, cfgs = build('sr', sr_kw, 3, lowres=True)
+    xs = torch.randn(B, 3, 32, 32, generator=g)
+    low = torch.randn(B, 3, 32, 32, generator=g)
+    lnt = torch.tensor([0.7093, 0.7093])
+    with torch.no_grad():
+        rs = us(xs, t, text_embeds=te, text_mask=tm, lowres_cond_img=low, lowres_noise_times=lnt)
+        os_ = unet_ref.unet_forward(sds, cfgs, xs, t, text_embeds=te, text_mask=tm, lowres_cond_img=low, lowres_noise_times=lnt)
+    d = _maxdiff(rs, os_)
+    print(f'[unet sr] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-5 * max(1., rs.abs().max().item())
+    torch.save(dict(kwargs=sr_kw, wseed=3, x=xs, t=t, text_embeds=te, text_mask=tm, lowres_cond_img=low,
+                    lowres_noise_times=lnt, out=rs), os.path.join(out_dir, 'unet_sr_dim32.pt'))
+
+    # ---------------------------------------------------------------- 3. DDPM sample trajectory (base, CFG)
+    imagen = ref.Imagen(unets=u, image_sizes=32, timesteps=6, text_embed_dim=64)
+    imagen.unets[0].load_state_dict(sd)
+    torch.manual_seed(11)
+    r_img = imagen.sample(text_embeds=te, cond_scale=3., use_tqdm=False)
+    torch.manual_seed(11)
+    trace = []
+    o_img = sampler_ref.imagen_sample([(sd, cfg)], (32,), text_embeds=te, timesteps=6, cond_scale=3., trace=trace)
+    d = _maxdiff(r_img, o_img)
+    print(f'[ddpm sample] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-4
+    torch.save(dict(kwargs=base_kw, wseed=0, text_embeds=te, seed=11, timesteps=6, cond_scale=3.,
+                    out=r_img, trace=torch.stack(trace)), os.path.join(out_dir, 'ddpm_sample_dim32.pt'))
+
+    # ---------------------------------------------------------------- 4. cascade DDPM sample (base 16 -> SR 32)
+    imagen2 = ref.Imagen(unets=(ref.Unet(**base_kw), ref.Unet(**sr_kw)), image_sizes=(16, 32), timesteps=3, text_embed_dim=64)
+    imagen2.unets[0].load_state_dict(sd)
+    imagen2.unets[1].load_state_dict(sds)
+    torch.manual_seed(5)
+    r_c2 = imagen2.sample(text_embeds=te, cond_scale=2., use_tqdm=False, return_all_unet_outputs=True)
+    torch.manual_seed(5)
+    o_c2 = sampler_ref.imagen_sample([(sd, cfg), (sds, cfgs)], (16, 32), text_embeds=te, timesteps=3, cond_scale=2.,
+                                     return_all_unet_outputs=True)
+    for a, b in zip(r_c2, o_c2):
+        d = _maxdiff(a, b)
+        print(f'[ddpm cascade {tuple(a.shape)}] ref-vs-oracle max|d| = {d:.3e}')
+        assert d < 1e-4
+    torch.save(dict(base_kwargs=base_kw, sr_kwargs=sr_kw, wseed_base=0, wseed_sr=3, text_embeds=te, seed=5, timesteps=3,
+                    cond_scale=2., outs=[o.clone() for o in r_c2]), os.path.join(out_dir, 'ddpm_cascade_dim32.pt'))
+
+    # ---------------------------------------------------------------- 5. Elucidated sample (base + cascade)
+    el = ref.ElucidatedImagen(unets=(ref.Unet(**base_kw), ref.Unet(**sr_kw)), image_sizes=(16, 32), text_embed_dim=64,
+                              num_sample_steps=4)
+    el.unets[0].load_state_dict(sd)
+    el.unets[1].load_state_dict(sds)
+    torch.manual_seed(9)
+    r_e = el.sample(text_embeds=te, cond_scale=2., use_tqdm=False)
+    torch.manual_seed(9)
+    o_e = sampler_ref.elucidated_sample([(sd, cfg), (sds, cfgs)], (16, 32), text_embeds=te, cond_scale=2.,
+                                        hparams=dict(num_sample_steps=4))
+    d = _maxdiff(r_e, o_e)
+    print(f'[edm cascade] ref-vs-oracle max|d| = {d:.3e}')
+    # sigma_max=80 puts |x| ~ 80 in fp32 (1 ulp = 7.6e-6) and the untrained net amplifies it
+    # over 7 Heun evals x 2 stages: measured 7.6e-6 after 2 steps, ~5e-5 after 4, 2.3e-4 here.
+    assert d < 1e-3
+    torch.save(dict(base_kwargs=base_kw, sr_kwargs=sr_kw, wseed_base=0, wseed_sr=3, text_embeds=te, seed=9,
+                    num_sample_steps=4, cond_scale=2., out=r_e), os.path.join(out_dir, 'edm_cascade_dim32.pt'))
+
+    # ---------------------------------------------------------------- 6. schedule / scalar known answers
+    tt = torch.tensor([1., .75, .5, .25, 0., 0.2])
+    torch.save(dict(t=tt, cosine=ref.imagen_pytorch.alpha_cosine_log_snr(tt), linear=ref.imagen_pytorch.beta_linear_log_snr(tt),
+                    edm_sigmas=el.sample_schedule(4, 7, 0.002, 80)), os.path.join(out_dir, 'schedules.pt'))
+
+    # ---------------------------------------------------------------- 7. state_dict key/shape contract of the default configs
+    contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr']}
+    for name, kw in (('base_dim128', dict(dim=128)), ('base_dim32', dict(dim=32, dim_mults=(1, 2, 4, 8)))):
+        torch.manual_seed(0)
+        m = ref.Unet(**kw)
+        contract[name] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    torch.manual_seed(0)
+    m = ref.SRUnet256(lowres_cond=True)
+    contract['srunet256'] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    torch.save(contract, os.path.join(out_dir, 'state_dict_contract.pt'))
+    print('golden fixtures written to', out_dir)
+    for f in sorted(os.listdir(out_dir)):
+        print('  ', f, os.path.getsize(os.path.join(out_dir, f)) // 1024, 'KiB')
+
+
+if __name__ == '__main__':
+    main()
