@@ -1,0 +1,43 @@
+// Error plumbing + device checks of the C-ABI (include/b200_imagen.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void b200_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+extern "C" int b200_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(b200_src);
+    case 1: return (int)sizeof(b200_seg);
+    case 2: return (int)sizeof(b200_epilogue);
+    case 3: return (int)sizeof(b200_timerow_job);
+    case 4: return (int)sizeof(b200_ddpm_coef);
+    case 5: return (int)sizeof(b200_edm_coef);
+    default: return -1;
+  }
+}
+
+extern "C" int b200_check_device(int dev) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= dev) {
+    b200_set_error("no CUDA device %d (count %d)", dev, n);
+    cudaGetLastError();
+    return B200_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp p;
+  B200_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+  if (p.major != 10) {
+    b200_set_error("device %d is sm_%d%d; libb200imagen is built for sm_100a only", dev, p.major, p.minor);
+    return B200_ERR_NO_DEVICE;
+  }
+  return B200_OK;
+}

@@ -1,0 +1,515 @@
+// HBM-bound row-wise kernels on NHWC bf16 pixel rows: ChanRMSNorm+FiLM+SiLU, LayerNorm(+residual),
+// GlobalContext gate, gate*x+residual, layout gathers, per-step time-conditioning plumbing.
+// Reference arithmetic replaced: see include/b200_imagen.h next to each entry point.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ROW_THREADS = 256;
+constexpr int MAX_VPT = 16;  // 16-byte vectors cached per thread -> C <= 32*16*8 = 4096
+
+int pick_tpr(int vecs) {
+  int t = 1;
+  while (t * 2 <= vecs && t * 2 <= 32) t *= 2;
+  return t;
+}
+
+template <int TPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = TPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct RmsParams {
+  const __nv_bfloat16* src0;
+  const __nv_bfloat16* src1;
+  int C0, C1, ld0, ld1;
+  float scale1;
+  const float* gamma;  // [Ctot], already multiplied by sqrt(Ctot)
+  const float* film;   // [B, film_ld] or null
+  int film_ld, rows_per_sample;
+  __nv_bfloat16* out;
+  int ldo;
+  long long M;
+};
+
+template <int TPR>
+__global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParams p) {
+  const int rows_per_block = ROW_THREADS / TPR;
+  const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int Ctot = p.C0 + p.C1;
+  const int vecs = Ctot >> 3;
+  const bool active = row < p.M;
+  uint4 buf[MAX_VPT];
+  float ss = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < MAX_VPT; ++i) {
+      const int v = t + i * TPR;
+      if (v < vecs) {
+        const int c = v << 3;
+        float f[8];
+        if (c < p.C0) {
+          buf[i] = __ldg(reinterpret_cast<const uint4*>(p.src0 + row * p.ld0 + c));
+          unpack8(buf[i], f);
+        } else {
+          buf[i] = __ldg(reinterpret_cast<const uint4*>(p.src1 + row * p.ld1 + (c - p.C0)));
+          unpack8(buf[i], f);
+        }
+        const float sc = c < p.C0 ? 1.f : p.scale1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float x = f[j] * sc; ss += x * x; }
+      }
+    }
+  }
+  ss = group_sum<TPR>(ss);
+  if (!active) return;
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  const float* film = p.film != nullptr ? p.film + (row / p.rows_per_sample) * (long long)p.film_ld : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAX_VPT; ++i) {
+    const int v = t + i * TPR;
+    if (v < vecs) {
+      const int c = v << 3;
+      float f[8];
+      unpack8(buf[i], f);
+      const float sc = (c < p.C0 ? 1.f : p.scale1) * inv;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = f[j] * sc * __ldg(p.gamma + c + j);
+        if (film != nullptr) y = y * (__ldg(film + c + j) + 1.f) + __ldg(film + Ctot + c + j);
+        f[j] = silu_f(y);
+      }
+      *reinterpret_cast<uint4*>(p.out + row * p.ldo + c) = pack8(f);
+    }
+  }
+}
+
+struct LnParams {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* residual;
+  const float* g;
+  const float* beta;
+  __nv_bfloat16* out;
+  int ldx, ldr, ldo, C;
+  float eps;
+  long long M;
+};
+
+template <int TPR>
+__global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
+  const int rows_per_block = ROW_THREADS / TPR;
+  const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int vecs = p.C >> 3;
+  const bool active = row < p.M;
+  uint4 buf[MAX_VPT];
+  float s = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < MAX_VPT; ++i) {
+      const int v = t + i * TPR;
+      if (v < vecs) {
+        buf[i] = __ldg(reinterpret_cast<const uint4*>(p.x + row * p.ldx + (v << 3)));
+        float f[8];
+        unpack8(buf[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+      }
+    }
+  }
+  s = group_sum<TPR>(s);
+  const float mean = s / (float)p.C;
+  float vs = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < MAX_VPT; ++i) {
+      const int v = t + i * TPR;
+      if (v < vecs) {
+        float f[8];
+        unpack8(buf[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; vs += d * d; }
+      }
+    }
+  }
+  vs = group_sum<TPR>(vs);
+  if (!active) return;
+  const float rstd = rsqrtf(vs / (float)p.C + p.eps);
+#pragma unroll
+  for (int i = 0; i < MAX_VPT; ++i) {
+    const int v = t + i * TPR;
+    if (v < vecs) {
+      const int c = v << 3;
+      float f[8];
+      unpack8(buf[i], f);
+      float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.residual != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + c)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = (f[j] - mean) * rstd * __ldg(p.g + c + j);
+        if (p.beta != nullptr) y += __ldg(p.beta + c + j);
+        f[j] = y + r[j];
+      }
+      *reinterpret_cast<uint4*>(p.out + row * p.ldo + c) = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- GlobalContext
+
+constexpr int GCA_WARPS = 8;
+constexpr int GCA_MAX_VPL = 8;  // vectors of 8 channels per lane -> C <= 2048
+
+__global__ void __launch_bounds__(GCA_WARPS * 32) gca_pool_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows_per_sample,
+                                                                  int C, const float* __restrict__ wk, float bk, int nchunk,
+                                                                  float* __restrict__ scratch) {
+  extern __shared__ float gsm[];  // [GCA_WARPS][C + 2] then wk[C]
+  float* swk = gsm + GCA_WARPS * (C + 2);
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) swk[c] = wk[c];
+  __syncthreads();
+  const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
+  const int p0 = chunk * ppc, p1 = min(rows_per_sample, p0 + ppc);
+  const int vecs = C >> 3;
+  float acc[GCA_MAX_VPL][8];
+#pragma unroll
+  for (int i = 0; i < GCA_MAX_VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int px = p0 + warp; px < p1; px += GCA_WARPS) {
+    const __nv_bfloat16* xr = x + ((long long)b * rows_per_sample + px) * ldx;
+    float f[GCA_MAX_VPL][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < GCA_MAX_VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < vecs) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + (v << 3))), f[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot += f[i][j] * swk[(v << 3) + j];
+      }
+    }
+    const float logit = warp_sum(dot) + bk;
+    const float m_new = fmaxf(m, logit);
+    const float sc = __expf(m - m_new), pw = __expf(logit - m_new);
+    m = m_new;
+    l = l * sc + pw;
+#pragma unroll
+    for (int i = 0; i < GCA_MAX_VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = acc[i][j] * sc + pw * f[i][j];
+      }
+    }
+  }
+  float* mine = gsm + warp * (C + 2);
+  if (lane == 0) { mine[0] = m; mine[1] = l; }
+#pragma unroll
+  for (int i = 0; i < GCA_MAX_VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine[2 + (v << 3) + j] = acc[i][j];
+    }
+  }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < GCA_WARPS; ++w) M = fmaxf(M, gsm[w * (C + 2)]);
+  float* out = scratch + ((long long)b * nchunk + chunk) * (C + 2);
+  for (int c = threadIdx.x; c < C + 2; c += blockDim.x) {
+    if (c == 0) { out[0] = M; continue; }
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < GCA_WARPS; ++w) {
+      const float mw = gsm[w * (C + 2)];
+      const float e = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+      s += gsm[w * (C + 2) + c] * e;
+    }
+    out[c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) gca_finish_kernel(const float* __restrict__ scratch, int nchunk, int C, int hidden,
+                                                         const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float* __restrict__ gate) {
+  extern __shared__ float fsm[];  // pooled[C], hid[hidden]
+  float* pooled = fsm;
+  float* hid = fsm + C;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const float* sc = scratch + (long long)b * nchunk * (C + 2);
+  float M = -INFINITY;
+  for (int k = 0; k < nchunk; ++k) M = fmaxf(M, sc[(long long)k * (C + 2)]);
+  float L = 0.f;
+  for (int k = 0; k < nchunk; ++k) {
+    const float mk = sc[(long long)k * (C + 2)];
+    if (mk != -INFINITY) L += sc[(long long)k * (C + 2) + 1] * __expf(mk - M);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+      const float mk = sc[(long long)k * (C + 2)];
+      if (mk != -INFINITY) a += sc[(long long)k * (C + 2) + 2 + c] * __expf(mk - M);
+    }
+    pooled[c] = a / L;
+  }
+  __syncthreads();
+  for (int j = warp; j < hidden; j += nwarp) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __ldg(w1 + (long long)j * C + c) * pooled[c];
+    s = warp_sum(s);
+    if (lane == 0) hid[j] = silu_f(s + b1[j]);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nwarp) {
+    float s = 0.f;
+    for (int j = lane; j < hidden; j += 32) s += __ldg(w2 + (long long)c * hidden + j) * hid[j];
+    s = warp_sum(s);
+    if (lane == 0) gate[(long long)b * C + c] = sigmoid_f(s + b2[c]);
+  }
+}
+
+__global__ void gate_residual_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gate,
+                                     const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out, int ldo,
+                                     long long M, int C, int rows_per_sample) {
+  const int vecs = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * vecs) return;
+  const long long row = idx / vecs;
+  const int c = (int)(idx % vecs) << 3;
+  const int b = (int)(row / rows_per_sample);
+  float f[8], r[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + c)), f);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * ldr + c)), r);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * C + c));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (long long)b * C + c + 4));
+  f[0] = f[0] * g0.x + r[0]; f[1] = f[1] * g0.y + r[1]; f[2] = f[2] * g0.z + r[2]; f[3] = f[3] * g0.w + r[3];
+  f[4] = f[4] * g1.x + r[4]; f[5] = f[5] * g1.y + r[5]; f[6] = f[6] * g1.z + r[6]; f[7] = f[7] * g1.w + r[7];
+  *reinterpret_cast<uint4*>(out + row * ldo + c) = pack8(f);
+}
+
+// ---------------------------------------------------------------- layout gathers
+
+__global__ void im2col_init_kernel(const float* __restrict__ img0, int C0, const float* __restrict__ img1, int C1, int B, int H, int W,
+                                   int ks, __nv_bfloat16* __restrict__ out, int Kpad) {
+  const int vecs = Kpad >> 3;
+  const long long M = (long long)B * H * W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * vecs) return;
+  const long long row = idx / vecs;
+  const int k0 = (int)(idx % vecs) << 3;
+  const int w = (int)(row % W), h = (int)((row / W) % H), b = (int)(row / ((long long)W * H));
+  const int Cin = C0 + C1, pad = ks / 2, K = ks * ks * Cin;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = k0 + j;
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / Cin, c = k - tap * Cin;
+      const int hh = h + tap / ks - pad, ww = w + tap % ks - pad;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        v = c < C0 ? __ldg(img0 + (((long long)b * C0 + c) * H + hh) * W + ww)
+                   : __ldg(img1 + (((long long)b * C1 + (c - C0)) * H + hh) * W + ww);
+      }
+    }
+    f[j] = v;
+  }
+  *reinterpret_cast<uint4*>(out + row * Kpad + k0) = pack8(f);
+}
+
+__global__ void pixel_unshuffle_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W, int C,
+                                       __nv_bfloat16* __restrict__ out) {
+  const int H2 = H / 2, W2 = W / 2, vecs = (4 * C) >> 3;
+  const long long M2 = (long long)B * H2 * W2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M2 * vecs) return;
+  const long long orow = idx / vecs;
+  const int k = (int)(idx % vecs) << 3;
+  const int s = k / C, c = k - s * C;  // s = s1*2 + s2
+  const int w2 = (int)(orow % W2), h2 = (int)((orow / W2) % H2), b = (int)(orow / ((long long)W2 * H2));
+  const long long irow = ((long long)b * H + 2 * h2 + (s >> 1)) * W + 2 * w2 + (s & 1);
+  *reinterpret_cast<uint4*>(out + orow * (4 * C) + k) = __ldg(reinterpret_cast<const uint4*>(x + irow * ldx + c));
+}
+
+__global__ void nchw_to_rows_kernel(const float* __restrict__ img, int B, int C, int H, int W, __nv_bfloat16* __restrict__ out, int Cpad) {
+  const long long M = (long long)B * H * W;
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const int w = (int)(row % W), h = (int)((row / W) % H), b = (int)(row / ((long long)W * H));
+  for (int c = 0; c < Cpad; ++c) {
+    const float v = c < C ? __ldg(img + (((long long)b * C + c) * H + h) * W + w) : 0.f;
+    out[row * Cpad + c] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------- per-step conditioning plumbing
+
+__global__ void make_time_cond_kernel(const float* __restrict__ table, const float* __restrict__ th, const int* __restrict__ slots, int R,
+                                      int D, __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * D) return;
+  const int r = (int)(idx / D), d = (int)(idx % D);
+  const float v = table[(long long)slots[r] * D + d] + th[idx];
+  out[idx] = __float2bfloat16(silu_f(v));
+}
+
+__global__ void update_time_rows_kernel(const b200_timerow_job* __restrict__ jobs, const int* __restrict__ slots) {
+  const b200_timerow_job j = jobs[blockIdx.x];
+  const int b = blockIdx.y;
+  const int n = j.rows * j.width;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(j.table) + (long long)slots[b] * n;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst) + (long long)b * j.sample_stride;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace
+
+#define DISPATCH_TPR(tpr, KERNEL, grid_rows, ...)                                                       \
+  switch (tpr) {                                                                                         \
+    case 1: KERNEL<1><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 1), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
+    case 2: KERNEL<2><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 2), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
+    case 4: KERNEL<4><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 4), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
+    case 8: KERNEL<8><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 8), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
+    case 16: KERNEL<16><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 16), ROW_THREADS, 0, st>>>(__VA_ARGS__); break; \
+    default: KERNEL<32><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 32), ROW_THREADS, 0, st>>>(__VA_ARGS__); break; \
+  }
+
+extern "C" int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1_scale, const float* gamma_sqrtC, const float* film,
+                                      int32_t film_ld, int32_t rows_per_sample, void* out, int32_t ldo, int64_t M, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(nsrc == 1 || nsrc == 2, "rmsnorm: nsrc must be 1 or 2");
+  B200_REQUIRE(M > 0 && out && gamma_sqrtC, "rmsnorm: bad args");
+  RmsParams p;
+  p.src0 = reinterpret_cast<const __nv_bfloat16*>(srcs[0].ptr); p.C0 = srcs[0].C; p.ld0 = srcs[0].ld;
+  p.src1 = nsrc == 2 ? reinterpret_cast<const __nv_bfloat16*>(srcs[1].ptr) : nullptr;
+  p.C1 = nsrc == 2 ? srcs[1].C : 0; p.ld1 = nsrc == 2 ? srcs[1].ld : 0;
+  p.scale1 = src1_scale; p.gamma = gamma_sqrtC; p.film = film; p.film_ld = film_ld;
+  p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.M = M;
+  const int Ctot = p.C0 + p.C1;
+  B200_REQUIRE((p.C0 & 7) == 0 && (p.C1 & 7) == 0 && (p.ld0 & 7) == 0 && (p.ld1 & 7) == 0 && (ldo & 7) == 0,
+               "rmsnorm: channel counts and strides must be multiples of 8 (C0=%d C1=%d)", p.C0, p.C1);
+  const int vecs = Ctot >> 3;
+  const int tpr = pick_tpr(vecs);
+  B200_REQUIRE((vecs + tpr - 1) / tpr <= MAX_VPT, "rmsnorm: C=%d too large", Ctot);
+  DISPATCH_TPR(tpr, rmsnorm_film_silu_kernel, M, p);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_layernorm(const void* x, int32_t ldx, const float* g, const float* beta, float eps, const void* residual, int32_t ldr,
+                              void* out, int32_t ldo, int64_t M, int32_t C, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && g && out && M > 0 && C > 0, "layernorm: bad args");
+  B200_REQUIRE((C & 7) == 0 && (ldx & 7) == 0 && (ldo & 7) == 0 && (residual == nullptr || (ldr & 7) == 0), "layernorm: C=%d / strides must be multiples of 8", C);
+  LnParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.g = g; p.beta = beta; p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldx = ldx; p.ldr = ldr; p.ldo = ldo; p.C = C; p.eps = eps; p.M = M;
+  const int vecs = C >> 3;
+  const int tpr = pick_tpr(vecs);
+  B200_REQUIRE((vecs + tpr - 1) / tpr <= MAX_VPT, "layernorm: C=%d too large", C);
+  DISPATCH_TPR(tpr, layernorm_kernel, M, p);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_gca_nchunk(int32_t rows_per_sample) {
+  int n = rows_per_sample / 256;
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  return n;
+}
+
+extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C, const float* wk, float bk,
+                             const float* w1, const float* b1, int32_t hidden, const float* w2, const float* b2, float* scratch,
+                             int32_t nchunk, float* gate, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && wk && w1 && b1 && w2 && b2 && scratch && gate, "gca: null pointer");
+  B200_REQUIRE((C & 7) == 0 && C <= 32 * 8 * GCA_MAX_VPL && (ldx & 7) == 0, "gca: C=%d unsupported", C);
+  B200_REQUIRE(nchunk >= 1 && B >= 1 && B <= 65535, "gca: bad nchunk/B");
+  const int smem1 = (GCA_WARPS * (C + 2) + C) * (int)sizeof(float);
+  static int smem1_cfg = 0;
+  if (smem1 > 48 * 1024 && smem1 > smem1_cfg) {
+    B200_CUDA_OK(cudaFuncSetAttribute(gca_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    smem1_cfg = smem1;
+  }
+  gca_pool_kernel<<<dim3(nchunk, B), GCA_WARPS * 32, smem1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, wk, bk,
+                                                                   nchunk, scratch);
+  B200_LAUNCH_OK();
+  const int smem2 = (C + hidden) * (int)sizeof(float);
+  gca_finish_kernel<<<B, 256, smem2, st>>>(scratch, nchunk, C, hidden, w1, b1, w2, b2, gate);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_gate_residual(const void* x, int32_t ldx, const float* gate, const void* residual, int32_t ldr, void* out, int32_t ldo,
+                                  int64_t M, int32_t C, int32_t rows_per_sample, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && gate && residual && out, "gate_residual: null pointer");
+  B200_REQUIRE((C & 7) == 0 && (ldx & 7) == 0 && (ldr & 7) == 0 && (ldo & 7) == 0, "gate_residual: C/strides must be multiples of 8");
+  const long long tot = M * (C >> 3);
+  gate_residual_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, gate,
+                                                                        reinterpret_cast<const __nv_bfloat16*>(residual), ldr,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C, rows_per_sample);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_im2col_init(const float* img0, int C0, const float* img1, int C1, int B, int H, int W, int ksize, void* out, int32_t Kpad,
+                                void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1), "im2col: null pointer");
+  B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
+  const long long tot = (long long)B * H * W * (Kpad >> 3);
+  im2col_init_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(img0, C0, img1, C1, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_pixel_unshuffle(const void* x, int32_t ldx, int B, int H, int W, int C, void* out, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && out && (C & 7) == 0 && (ldx & 7) == 0 && (H & 1) == 0 && (W & 1) == 0, "pixel_unshuffle: bad args (C=%d H=%d W=%d)", C, H, W);
+  const long long tot = (long long)B * (H / 2) * (W / 2) * ((4 * C) >> 3);
+  pixel_unshuffle_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H, W, C,
+                                                                          reinterpret_cast<__nv_bfloat16*>(out));
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_nchw_to_rows(const float* img, int B, int C, int H, int W, void* out, int32_t Cpad, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(img && out && Cpad >= C, "nchw_to_rows: bad args");
+  const long long M = (long long)B * H * W;
+  nchw_to_rows_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(img, B, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), Cpad);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_make_time_cond(const float* table, const float* text_hiddens, const int32_t* slots, int R, int32_t D, void* out, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(table && text_hiddens && slots && out && R > 0 && D > 0, "make_time_cond: bad args");
+  const long long tot = (long long)R * D;
+  make_time_cond_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(table, text_hiddens, slots, R, D, reinterpret_cast<__nv_bfloat16*>(out));
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_update_time_rows(const b200_timerow_job* jobs_dev, int njobs, const int32_t* slots, int R, int32_t max_elems, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (njobs == 0) return B200_OK;
+  B200_REQUIRE(jobs_dev && slots && R > 0 && R <= 65535, "update_time_rows: bad args");
+  int threads = max_elems >= 256 ? 256 : (max_elems >= 128 ? 128 : 64);
+  update_time_rows_kernel<<<dim3(njobs, R), threads, 0, st>>>(jobs_dev, slots);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}

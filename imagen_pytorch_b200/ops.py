@@ -1,0 +1,79 @@
+"""Thin, allocation-explicit Python wrappers over the C-ABI (used by UnetPlan and by the kernel tests)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Src, Seg, Epilogue
+
+BF16 = torch.bfloat16
+
+
+def ceil_to(a, b):
+    return (a + b - 1) // b * b
+
+
+def pack_weight(mats, N, device):
+    """mats: list of [N, C_seg] fp32 (one per K segment) -> bf16 [Npad, sum ceil64(C_seg)], K-major, zero padded."""
+    Np = _lib.npad(N)
+    cols = [ceil_to(m.shape[1], 64) for m in mats]
+    out = torch.zeros(Np, sum(cols), dtype=torch.float32, device=device)
+    o = 0
+    for m, c in zip(mats, cols):
+        out[:N, o:o + m.shape[1]] = m
+        o += c
+    return out.to(BF16).contiguous()
+
+
+def conv_taps(k):
+    r = k // 2
+    return [(dh, dw) for dh in range(-r, r + 1) for dw in range(-r, r + 1)]
+
+
+def conv_segments(Wt, split):
+    """k x k conv (pad k//2) over a channel concat: returns (segs, mats) in the K order the kernel walks."""
+    k = Wt.shape[-1]
+    segs, mats = [], []
+    for (dh, dw) in conv_taps(k):
+        o = 0
+        for i, c in enumerate(split):
+            segs.append((i, dh, dw))
+            mats.append(Wt[:, o:o + c, dh + k // 2, dw + k // 2])
+            o += c
+    return segs, mats
+
+
+class GemmCall:
+    """Prebuilt argument pack of one b200_conv_gemm launch; call(stream) enqueues it."""
+
+    def __init__(self, srcs, segs, grid, wpacked, N, out_ptr, *, bias=None, act=0, out_scale=1.0, residual=None, ldr=0,
+                 out_mode=_lib.OUT_BF16, ldc=0, out2_ptr=None, ldc2=0, split_col=0, rows_per_group=0, group_stride=0, row_offset=0,
+                 l2_cols=0, l2_scale=None, ps_C=0, dup_rows=0, impl=_lib.IMPL_TCGEN05, scratch_ptr=None):
+        """srcs: list of (ptr, C, ld); segs: list of (src, dh, dw); grid: (B, H, W) of the output pixel rows."""
+        self.lib = _lib.load()
+        self.keep = [wpacked, bias, l2_scale]
+        self.sa = (Src * len(srcs))(*[Src(p, c, ld) for (p, c, ld) in srcs])
+        self.ga = (Seg * len(segs))(*[Seg(*g) for g in segs])
+        e = Epilogue()
+        e.bias = bias.data_ptr() if bias is not None else None
+        e.act, e.out_scale = act, out_scale
+        e.residual, e.ldr = residual, ldr
+        e.out_mode, e.out, e.ldc = out_mode, out_ptr, ldc
+        e.out2, e.ldc2, e.split_col = out2_ptr, ldc2, split_col
+        e.rows_per_group, e.group_stride, e.row_offset = rows_per_group, group_stride, row_offset
+        e.l2_cols = l2_cols
+        e.l2_scale = l2_scale.data_ptr() if l2_scale is not None else None
+        e.ps_C, e.dup_rows = ps_C, dup_rows
+        self.e = e
+        self.args = (self.sa, len(srcs), self.ga, len(segs), grid[0], grid[1], grid[2], wpacked.data_ptr(), N, C.byref(e), impl, scratch_ptr)
+
+    def __call__(self, stream):
+        _lib.check(self.lib.b200_conv_gemm(*self.args, stream), 'b200_conv_gemm')
+
+
+def padded_bias(bias, N, device):
+    bp = torch.zeros(_lib.npad(N), dtype=torch.float32, device=device)
+    bp[:N] = bias
+    return bp

@@ -1,0 +1,281 @@
+/*
+ * b200_imagen.h -- C-ABI of libb200imagen.so: the sm_100a kernels behind the
+ * imagen-pytorch sampling hot path (U-Net forward x denoising loop).
+ *
+ * The reference (lucidrains/imagen-pytorch v2.0.0) has NO native/FFI interface:
+ * every FLOP goes through ATen.  The boundary a
+ * maintainer would bind is therefore "one entry point per fused ATen op group
+ * of Unet.forward / p_sample / one_unet_sample".  Each declaration below cites
+ * the reference lines (relative to /root/reference/imagen_pytorch/) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only: device pointers, sizes, strides, a
+ *     cudaStream_t passed as void*.  No torch types.
+ *   - every function returns 0 on success or a negative b200_status; the text
+ *     of the last error of the calling thread is b200_last_error().
+ *   - nothing here allocates, frees or synchronises: all functions are
+ *     CUDA-graph-capture safe.  The caller owns every buffer.
+ *   - activations are NHWC bf16 ("pixel rows": [B*H*W, C] row-major with an
+ *     explicit row stride ld, in elements); sampler state is fp32 NCHW exactly
+ *     as the reference keeps it.
+ */
+#ifndef B200_IMAGEN_H_
+#define B200_IMAGEN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  B200_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  B200_ERR_NO_DEVICE = -3, /* no sm_100 device */
+} b200_status;
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* sizeof() of the ABI structs as compiled: 0 b200_src, 1 b200_seg, 2 b200_epilogue, 3 b200_timerow_job,
+ * 4 b200_ddpm_coef, 5 b200_edm_coef (lets a binding verify its struct mirrors). */
+int b200_sizeof(int which);
+/* 0 if device `dev` is compute capability 10.x, else B200_ERR_NO_DEVICE. */
+int b200_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores
+ * (TMA-staged NHWC tiles -> 128B-swizzled smem -> tcgen05.mma -> TMEM -> fused epilogue).
+ * Replaces: nn.Conv2d 3x3/1x1 in Block.project (imagen_pytorch.py:681,691), res_conv (:732,757),
+ * Downsample 1x1 (:639), PixelShuffleUpsample conv+SiLU+PixelShuffle (:611-617), Parallel (:1366),
+ * final_conv (:1436,1725), and every nn.Linear on pixel rows: to_q/to_kv/to_out (:521-532,539,591;
+ * :782-791,799,834), FeedForward (:976-979), time_mlp (:711-714,739).
+ *
+ *   out[m, n] = epilogue( sum_seg sum_c  A_seg[pixel(m) + (dh,dw), c] * Wp[n, k(seg,c)] )
+ * ------------------------------------------------------------------------------------------ */
+
+#define B200_MAX_SRC 4
+#define B200_MAX_SEG 24
+
+typedef struct {
+  const void* ptr; /* bf16, [B*H*W, C] pixel rows, row stride ld elements (ld % 8 == 0) */
+  int32_t C;       /* channels read from this source */
+  int32_t ld;
+} b200_src;
+
+typedef struct {
+  int32_t src; /* index into srcs[] */
+  int32_t dh;  /* tap offset, rows   (-1..1 for 3x3 pad 1, 0 for 1x1) */
+  int32_t dw;  /* tap offset, columns */
+} b200_seg;
+
+enum { B200_ACT_NONE = 0, B200_ACT_SILU = 1, B200_ACT_GELU = 2 };
+enum {
+  B200_OUT_BF16 = 0,         /* out[row, n] bf16, row stride ldc                                   */
+  B200_OUT_PIXEL_SHUFFLE = 1,/* N = 4*ps_C ordered (r1, r2, c'): out[b, 2h+r1, 2w+r2, c'] bf16     */
+  B200_OUT_F32_NCHW = 2,     /* out[b, n, h, w] fp32 (final conv -> sampler)                        */
+  B200_OUT_F32 = 3,          /* out[row, n] fp32, row stride ldc                                    */
+};
+
+typedef struct {
+  const float* bias;      /* [N] or NULL */
+  int32_t act;            /* B200_ACT_* applied after bias */
+  float out_scale;        /* multiplies the activated value (1.0 = none) */
+  const void* residual;   /* bf16 [M, ldr] added last, or NULL */
+  int32_t ldr;
+  int32_t out_mode;       /* B200_OUT_* */
+  void* out;
+  int32_t ldc;
+  /* columns >= split_col go to out2 (column n - split_col), bf16 row-major; 0 = off */
+  void* out2;
+  int32_t ldc2;
+  int32_t split_col;
+  /* row remap for out/out2: row' = (m / rows_per_group) * group_stride + row_offset + m % rows_per_group;
+     rows_per_group == 0 -> identity */
+  int32_t rows_per_group;
+  int32_t group_stride;
+  int32_t row_offset;
+  /* cosine-sim attention: L2-normalise each 64-column group of the first l2_cols columns
+     (F.normalize eps 1e-12) and multiply by l2_scale[n % 64]  (imagen_pytorch.py:559-561, 812-814) */
+  int32_t l2_cols;
+  const float* l2_scale;  /* [64] */
+  int32_t ps_C;           /* C' for B200_OUT_PIXEL_SHUFFLE */
+  /* also store rows at +dup_rows (classifier-free-guidance batch duplication); 0 = off */
+  int32_t dup_rows;
+} b200_epilogue;
+
+/* Packed weight layout: bf16 [Npad, Ktot], Npad = N rounded up to the N tile, K ordered by
+ * segment, each segment padded to a multiple of 64 channels with zeros.
+ * b200_conv_gemm_npad() tells the packer the N padding used for a given N. */
+int b200_conv_gemm_npad(int N);
+
+int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* segs, int nseg,
+                   int B, int H, int W,              /* pixel grid of the OUTPUT rows: M = B*H*W */
+                   const void* w_packed, int N,
+                   const b200_epilogue* epi,
+                   int impl,                         /* 0 = tcgen05 (product); 1 = SIMT checker used by tests */
+                   void* f32_scratch,                /* impl 1 only: >= M*Npad floats */
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Flash-style cosine-sim attention (no N x M score matrix).  Q rows are already L2-normalised
+ * and pre-multiplied by q_scale * 8 * log2(e) by the to_q epilogue; K rows by k_scale.
+ * Replaces: Attention.forward einsum/softmax/einsum (imagen_pytorch.py:565-588) with the multi-query
+ * layout (n_heads = 1, rows = 8*n, q_row_stride = 64) and CrossAttention.forward (:818-833)
+ * (n_heads = 8, rows = n, q_row_stride = 512, per-head K/V).
+ * problem (b, h): q + b*q_bs + h*q_hs (row stride q_rs), k/v + b*kv_bs + h*kv_hs (row stride kv_rs),
+ * o like q.  Head dim = 64.  All strides in elements.
+ * ------------------------------------------------------------------------------------------ */
+int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows,
+                   const void* k, const void* v, int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys,
+                   int B, int n_heads, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise normalisation kernels on pixel rows (HBM-bound).
+ * ------------------------------------------------------------------------------------------ */
+
+/* ChanRMSNorm -> FiLM -> SiLU over the channel concat of up to 2 sources
+ * (Block.forward imagen_pytorch.py:683-690, ChanRMSNorm :322-329, skip concat+scale :1694).
+ *   y = silu( x / max(||x||_2, 1e-12) * gamma_sqrtC[c] * (scale[b,c] + 1) + shift[b,c] )
+ * x = cat(src0, src1 * src1_scale).  film: fp32 [B, film_ld], scale at [c], shift at [Ctot + c]; NULL = none. */
+int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1_scale, const float* gamma_sqrtC,
+                           const float* film, int32_t film_ld, int32_t rows_per_sample,
+                           void* out, int32_t ldo, int64_t M, void* stream);
+
+/* LayerNorm over C (biased variance, eps): y = (x-mean)*rsqrt(var+eps)*g (+ beta) (+ residual).
+ * Custom gain-only LayerNorm imagen_pytorch.py:331-349 (eps 1e-5) and the "+ x" of Residual-style
+ * callers (:749, :1017-1018). */
+int b200_layernorm(const void* x, int32_t ldx, const float* g, const float* beta, float eps,
+                   const void* residual, int32_t ldr, void* out, int32_t ldo, int64_t M, int32_t C, void* stream);
+
+/* GlobalContext (imagen_pytorch.py:945-970): gate[b, c] = sigmoid(W2 silu(W1 pool + b1) + b2),
+ * pool[c] = sum_p softmax_p(x[p,:].wk + bk) x[p, c].  scratch: fp32 [B, nchunk, C + 2]. */
+int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C,
+                  const float* wk, float bk, const float* w1, const float* b1, int32_t hidden,
+                  const float* w2, const float* b2, float* scratch, int32_t nchunk, float* gate, void* stream);
+int b200_gca_nchunk(int32_t rows_per_sample);
+
+/* out = x * gate[b, c] + residual  (ResnetBlock.forward imagen_pytorch.py:755-757). */
+int b200_gate_residual(const void* x, int32_t ldx, const float* gate, const void* residual, int32_t ldr,
+                       void* out, int32_t ldo, int64_t M, int32_t C, int32_t rows_per_sample, void* stream);
+
+/* Patch gather for the initial cross-embed convolution (CrossEmbedLayer imagen_pytorch.py:1051-1076,
+ * used at :1564): fp32 NCHW image(s) -> bf16 [B*H*W, Kpad] rows ordered (kh, kw, c), zero padded.
+ * c runs over cat(img0, img1) (lowres concat :1551). */
+int b200_im2col_init(const float* img0, int C0, const float* img1, int C1, int B, int H, int W, int ksize,
+                     void* out, int32_t Kpad, void* stream);
+
+/* Pixel-unshuffle gather of Downsample (imagen_pytorch.py:638): out[b,h,w,(s1,s2,c)] = x[b,2h+s1,2w+s2,c]. */
+int b200_pixel_unshuffle(const void* x, int32_t ldx, int B, int H, int W, int C, void* out, void* stream);
+
+/* fp32 NCHW [B,C,H,W] -> bf16 NHWC rows with Cpad channels (zero padded). Used for the low-res
+ * conditioning image concatenated before final_conv (imagen_pytorch.py:1722-1723). */
+int b200_nchw_to_rows(const float* img, int B, int C, int H, int W, void* out, int32_t Cpad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-step conditioning plumbing (time-dependent rows only; everything text-dependent is
+ * hoisted out of the loop).
+ * ------------------------------------------------------------------------------------------ */
+
+/* t_silu[r, :] = silu(time_cond_table[slot[r], :] + text_hiddens[r, :])   bf16 out.
+ * (Unet.forward :1578,1588,1652 and the nn.SiLU at the head of every time_mlp :711-713.) */
+int b200_make_time_cond(const float* table, const float* text_hiddens, const int32_t* slots,
+                        int R, int32_t D, void* out, void* stream);
+
+typedef struct {
+  const void* table; /* bf16 [S, rows, width] : time-token K or V rows for every schedule slot */
+  void* dst;         /* bf16, row r of sample b at dst + b*sample_stride + r*width */
+  int64_t sample_stride;
+  int32_t rows;
+  int32_t width;
+} b200_timerow_job;
+
+/* For every job and sample: copy table[slot[b]] into the K/V buffers. jobs is a DEVICE array. */
+int b200_update_time_rows(const b200_timerow_job* jobs_dev, int njobs, const int32_t* slots, int R,
+                          int32_t max_elems, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 conditioning head (runs once per sample() call, not per step): time MLPs, text_to_cond,
+ * PerceiverResampler, to_text_non_attn_cond, norm_cond, per-layer context K/V.
+ * Unet.forward imagen_pytorch.py:1573-1660; PerceiverAttention :408-445; LearnedSinusoidalPosEmb :664-669.
+ * ------------------------------------------------------------------------------------------ */
+
+/* y[M,N] = out_act( in_act(x)[M,K] @ W[N,K]^T + b ) (+ residual), all fp32. */
+int b200_linear_f32(const float* x, int32_t ldx, const float* W, const float* b, int in_act, int out_act,
+                    const float* residual, int32_t ldr, float* y, int32_t ldy, int64_t M, int32_t N, int32_t K,
+                    void* stream);
+int b200_layernorm_f32(const float* x, int32_t ldx, const float* g, const float* beta, float eps,
+                       float* y, int32_t ldy, int64_t M, int32_t C, void* stream);
+/* [x, sin(2 pi x w), cos(2 pi x w)] -> out[M, 2*half+1] */
+int b200_sinu_pos_emb(const float* x, const float* w, int M, int half, float* out, void* stream);
+/* multi-head cosine-sim attention, fp32: q [B, nq, H*64], k/v [B, nk, H*64] (ld = row strides). */
+int b200_attn_f32(const float* q, int32_t ldq, const float* k, const float* v, int32_t ldkv,
+                  const float* q_scale, const float* k_scale, float* o, int32_t ldo,
+                  int B, int H, int nq, int nk, void* stream);
+/* per 64-wide head group: optional F.normalize, optional * scale[64], cast to bf16 and scatter:
+ * dst[(row / rpg) * s_grp + (row % rpg) * s_row + g * s_head + d]. */
+int b200_headnorm_store(const float* x, int32_t ldx, int32_t col0, int32_t ngroups, int normalize,
+                        const float* scale, void* dst, int32_t rpg, int64_t s_grp, int64_t s_row, int64_t s_head,
+                        int64_t M, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler steps (fp32 state, exact torch.quantile dynamic thresholding inside).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Per-step scalars of the continuous-time DDPM posterior, tabulated on the host with the same
+ * torch ops as GaussianDiffusionContinuousTimes (imagen_pytorch.py:245-270, 314-318). */
+typedef struct {
+  float sigma;          /* sqrt(sigmoid(-log_snr(t)))           */
+  float alpha;          /* sqrt(sigmoid( log_snr(t)))           */
+  float inv_alpha_clamped; /* 1 / max(alpha, 1e-8)              */
+  float alpha_next;
+  float c;              /* -expm1(log_snr - log_snr_next)        */
+  float noise_std;      /* [t_next != 0] * exp(0.5*log(max(sigma_next^2 c, 1e-20))) */
+  float pad0, pad1;
+} b200_ddpm_coef;
+
+/* One ancestral DDPM step, in place on x (Imagen.p_sample imagen_pytorch.py:2112-2165,
+ * p_mean_variance :2085-2110, CFG combine :1522).  pred: fp32 [R, C, H, W] with the conditional rows
+ * first and (if cond_scale != 1) the null rows at +B.  objective 0 noise, 1 x_start, 2 v.
+ * thresholding: 1 = dynamic (quantile q_lo/q_hi/q_w as torch.quantile computes them), 0 = clamp(-1,1).
+ * Increments slots[0..R) by one at the end (the device-side step counter). */
+int b200_ddpm_step(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs,
+                   int32_t* slots, int R, int B, int64_t chw, float cond_scale, int objective,
+                   int thresholding, int32_t q_lo, int32_t q_hi, float q_w, void* stream);
+
+typedef struct {
+  float s_noise;     /* S_noise: eps = s_noise * z                                        */
+  float noise_coef;  /* fp32(sqrt(sigma_hat^2 - sigma^2)) (python double math, then cast) */
+  float sigma_hat, sigma_next;               /* fp32 casts of the python doubles          */
+  float dt, half_dt; /* fp32(sigma_next - sigma_hat), fp32(0.5 * (sigma_next - sigma_hat)) */
+  float c_in_hat, c_skip_hat, c_out_hat;     /* preconditioning at sigma_hat (torch fp32 ops) */
+  float c_in_next, c_skip_next, c_out_next;  /* at sigma_next (unused on the last step)   */
+  float has_second;  /* sigma_next != 0 */
+  float pad0, pad1, pad2;
+} b200_edm_coef;
+
+/* EDM stochastic Heun sampler (ElucidatedImagen.one_unet_sample elucidated_imagen.py:481-531,
+ * preconditioned_network_forward :340-369, threshold_x_start :309-321), split at the two network
+ * evaluations.  phase 0: x_hat = x + noise_coef*(s_noise*z) ; net_in = c_in_hat * x_hat.
+ * phase 1: D = thr(c_skip x_hat + c_out F); d = (x_hat - D)/sigma_hat; x1 = x_hat + (sn - sh) d;
+ *          net_in = c_in_next * x1 (if has_second) else x = x1.
+ * phase 2: D' = thr(...x1...); d' = (x1 - D')/sn; x = x_hat + 0.5 (sn - sh)(d + d').
+ * The step index into coefs is read from the device counter step_ctr[0] (step_ctr is int32[2], both
+ * zero-initialised by the caller); the last phase of a step (2, or 1 when !has_second) stages the
+ * increment in step_ctr[1] and the next phase-0 launch commits it.  Phases 1 and 2 bump slots (one slot per network
+ * evaluation) so the whole step is CUDA-graph capturable. */
+int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, float* d, float* net_in,
+                   const float* pred, const float* eps, const b200_edm_coef* coefs, int32_t* step_ctr,
+                   int32_t* slots, int R, int B, int64_t chw, float cond_scale, int thresholding,
+                   int32_t q_lo, int32_t q_hi, float q_w, void* stream);
+
+/* out = (clamp(x, -1, 1) + 1) * 0.5 (imagen_pytorch.py:2281,2288) or just the clamp. */
+int b200_finalize_images(const float* x, float* out, int64_t n, int unnormalize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_IMAGEN_H_ */

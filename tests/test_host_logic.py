@@ -1,0 +1,83 @@
+"""CPU: host-side schedule tables, quantile rank arithmetic, weight packing and shard logic."""
+import math
+
+import pytest
+import torch
+
+from imagen_pytorch_b200 import ElucidatedImagen, Imagen, Unet
+from imagen_pytorch_b200.dist import shard_bounds
+from imagen_pytorch_b200.imagen import GaussianDiffusionContinuousTimes, quantile_ranks
+from imagen_pytorch_b200 import ops
+from oracle import sampler_ref
+
+
+@pytest.mark.parametrize('n', [12288, 3072, 196608, 10])
+def test_quantile_ranks_reproduce_torch_quantile(n):
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(3, n, generator=g).abs()
+    lo, hi, w = quantile_ranks(n, 0.95, 'cpu')
+    s = x.sort(dim=-1).values
+    a, b = s[:, lo], s[:, hi]
+    mine = torch.where(torch.tensor(w) < 0.5, a + w * (b - a), b - (b - a) * (1 - w))
+    assert torch.equal(mine, torch.quantile(x, 0.95, dim=-1))
+
+
+@pytest.mark.parametrize('schedule', ['cosine', 'linear'])
+def test_ddpm_coefficient_table_matches_oracle_posterior(schedule):
+    T = 7
+    sched = GaussianDiffusionContinuousTimes(noise_schedule=schedule, timesteps=T)
+    coefs, log_snr = sched.ddpm_coefficients('cpu')
+    fn = sampler_ref.LOG_SNR[schedule]
+    x_t, x0 = torch.randn(1, 3, 4, 4), torch.randn(1, 3, 4, 4)
+    for i, (t, tn) in enumerate(sampler_ref.sampling_timesteps(T, 1)):
+        mean, _, log_var = sampler_ref.q_posterior(fn, x0, x_t, t, tn)
+        sigma, alpha, _, alpha_next, c, noise_std = coefs[i, :6]
+        mine = alpha_next * (x_t * (1 - c) / alpha + c * x0)
+        assert torch.equal(mine, mean)
+        assert torch.equal(log_snr[i], fn(t)[0])
+        expect_std = (0.5 * log_var).exp().flatten()[0] * (0. if tn.item() == 0 else 1.)
+        assert torch.equal(noise_std, expect_std)
+    assert coefs[-1, 5] == 0            # no noise on the last step
+
+
+def test_edm_tables_match_oracle_schedule():
+    u = Unet(dim=32, dim_mults=(1, 2), text_embed_dim=64)
+    el = ElucidatedImagen(u, image_sizes=16, text_embed_dim=64, num_sample_steps=5)
+    hp = el.hparams[0]
+    coefs, times, init_sigma = el._edm_tables(hp, hp.sigma_min, hp.sigma_max, 'cpu')
+    sig = sampler_ref.edm_sample_schedule(5, 7, 0.002, 80)
+    assert init_sigma == sig[0] and coefs.shape == (5, 16) and times.numel() == 9   # 5 + 4 network evaluations
+    gamma = min(80 / 5, math.sqrt(2) - 1)
+    s0 = sig[0].item()
+    assert abs(coefs[0, 2].item() - (s0 + gamma * s0 if 0.05 <= s0 <= 50 else s0)) < 1e-5
+    assert coefs[-1, 12] == 0 and coefs[0, 12] == 1                                  # has_second
+    assert torch.allclose(times[0], torch.log(coefs[0, 2]) * 0.25)
+
+
+def test_weight_packing_layout():
+    W = torch.arange(2 * 5 * 3 * 3, dtype=torch.float32).view(2, 5, 3, 3)
+    segs, mats = ops.conv_segments(W, [2, 3])
+    assert len(segs) == 18 and segs[0] == (0, -1, -1) and segs[1] == (1, -1, -1) and segs[-1] == (1, 1, 1)
+    assert torch.equal(mats[0], W[:, :2, 0, 0]) and torch.equal(mats[-1], W[:, 2:, 2, 2])
+
+
+@pytest.mark.parametrize('n,world', [(512, 8), (10, 4), (3, 8), (16, 1)])
+def test_shard_bounds_partition_the_batch(n, world):
+    spans = [shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_sample_argument_validation_mirrors_reference():
+    u = Unet(dim=32, dim_mults=(1, 2), text_embed_dim=64)
+    im = Imagen(u, image_sizes=16, text_embed_dim=64, timesteps=2, cond_drop_prob=0.)
+    with pytest.raises(AssertionError):
+        im.sample(text_embeds=torch.randn(1, 8, 32), use_tqdm=False)          # wrong embedding dim
+    with pytest.raises(AssertionError):
+        im.sample(use_tqdm=False)                                               # text required
+    with pytest.raises(NotImplementedError):
+        im.sample(texts=['a cat'], use_tqdm=False)                              # T5 encoder out of scope
+    with pytest.raises(NotImplementedError):
+        im.sample(text_embeds=torch.randn(1, 8, 64), inpaint_images=torch.zeros(1, 3, 16, 16), inpaint_masks=torch.zeros(1, 16, 16), use_tqdm=False)
