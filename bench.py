@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the imagen sampling hot path on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: Imagen.sample() of `bs` images through the full
+T-step DDPM loop (classifier-free guidance => 2*bs U-Net rows per denoising step).  Workload at every N:
+BASELINE.json configs[1]: base Unet(dim=128) 64x64, bs=16 per GPU, 1000 DDPM steps, cond_scale=3.0,
+synthetic text_embeds (bs,256,768), random-init weights (final_conv re-randomised: the reference zero-inits it).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on this box's host cores
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks.  `value` = inputs resident in HBM; `e2e` = same call with pinned-host text_embeds copied in and the
+images copied back inside the timed region.  `roofline` = the dominant kernel (multi-query flash attention at the
+64x64 level, 59% of the algorithmic FLOPs) timed alone with CUDA events at the workload's exact shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work (SURVEY.md section 8d / BASELINE.md section 3; FlopCounterMode over the reference forward)
+GFLOP_PER_FORWARD_DIM128 = 131.90
+ATTN_L0_GFLOP_PER_SAMPLE = 2 * 2 * (8 * 4096) * (4096 + 39) * 64 / 1e9          # QK^T + PV of one 64x64 Attention block (:565,:588)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tensor_burst=d['bf16_tflops'], tensor_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f'/tmp/b200_clocks_{os.getpid()}.csv'
+
+    def __enter__(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200', '-i', str(self.index)],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.close()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [s.strip() for s in line.split(',')]
+                if len(p) < 9:
+                    continue
+                sm.append(float(p[1])); mx.append(float(p[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        except Exception:
+            pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def build_model(dim, timesteps, device):
+    import imagen_pytorch_b200 as b2
+    torch.manual_seed(0)
+    unet = b2.Unet(dim=dim)
+    with torch.no_grad():                                   # the reference zero-inits final_conv (imagen_pytorch.py:1438)
+        unet.final_conv.weight.normal_(0, 0.02)
+        unet.final_conv.bias.normal_(0, 0.02)
+    return b2.Imagen(unet, image_sizes=64, timesteps=timesteps).to(device)
+
+
+def time_attention_kernel(bs_rows, device, iters=10):
+    """The dominant kernel alone, at the workload's shape: one 64x64 multi-query self-attention block, R = 2*bs rows."""
+    from imagen_pytorch_b200 import _lib
+    import torch.nn.functional as F
+    n, heads, nk = 4096, 8, 4096 + 39
+    q = (F.normalize(torch.randn(bs_rows, heads * n, 64, device=device), dim=-1) * 8 * 1.4426950408889634).to(torch.bfloat16)
+    k = F.normalize(torch.randn(bs_rows, nk, 64, device=device), dim=-1).to(torch.bfloat16)
+    v = torch.randn(bs_rows, nk, 64, device=device).to(torch.bfloat16)
+    o = torch.empty_like(q)
+    st = torch.cuda.current_stream(device)
+    args = (q.data_ptr(), o.data_ptr(), heads * n * 64, 0, 64, heads * n, k.data_ptr(), v.data_ptr(), nk * 64, 0, 64, nk, bs_rows, 1, st.cuda_stream)
+    for _ in range(3):
+        _lib.call('b200_attention', *args)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(iters):                                  # q+o = 268 MB per launch > 126 MB L2: no explicit flush needed
+        _lib.call('b200_attention', *args)
+    e1.record(st)
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / iters
+
+
+def cpu_reference_step(dim, bs, threads=None):
+    """One DDPM denoising step (cond + null U-Net pass, CFG combine, thresholded posterior update) of the reference
+    algorithm on the host cores, through the oracle port.  Returns seconds."""
+    from oracle import unet_ref, sampler_ref
+    import imagen_pytorch_b200 as b2
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    u = b2.Unet(dim=dim)
+    sd = {k: v.detach().clone() for k, v in u.state_dict().items()}
+    sd['final_conv.weight'].normal_(0, 0.02)
+    cfg = unet_ref.unet_config(dim=dim)
+    te = torch.randn(bs, 256, 768)
+    fn = lambda x, t, cond_scale, lowres_noise_times=None, **k: unet_ref.unet_forward_with_cond_scale(sd, cfg, x, t, cond_scale=cond_scale, **k)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        sampler_ref.ddpm_p_sample_loop(fn, (bs, 3, 64, 64), timesteps=1, cond_scale=3., unet_kwargs=dict(text_embeds=te, text_mask=torch.ones(bs, 256, dtype=torch.bool)))
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bs = 1
+    for _ in range(args.warmup):
+        cpu_reference_step(args.dim, bs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(args.dim, bs)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = bs / (dt * args.timesteps)                      # one denoising step timed; a batch needs `timesteps` of them
+    sample = f'1 of {args.timesteps} DDPM denoising steps (cond+null U-Net pass, cond_scale 3.0) at bs={bs}, extrapolated x{args.timesteps}'
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3 * args.timesteps / bs * args.bs, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(args):
+    return {'workload': f'BASELINE.json configs[1]: base Unet dim={args.dim} 64x64, bs={args.bs}/GPU, {args.timesteps} DDPM steps, cond_scale=3.0 '
+                        f'(classifier-free guidance: {2 * args.bs} U-Net rows/step), random text_embeds ({args.bs},256,768)',
+            'global_batch': args.bs * args.gpus, 'parallelism': f'dp{args.gpus} (independent sample shards, one all-gather of finished images)',
+            'l2': 'no explicit flush: per-step activation working set (GBs) and the 268 MB q/o of the timed attention kernel exceed the 126 MB L2'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--bs', type=int, default=16)
+    ap.add_argument('--dim', type=int, default=128)
+    ap.add_argument('--timesteps', type=int, default=1000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py --impl b200 needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    assert args.warmup >= 3, 'timing hygiene: at least 3 warm-up steps'
+
+    from imagen_pytorch_b200.dist import all_gather_images
+    imagen = build_model(args.dim, args.timesteps, device)
+    torch.manual_seed(1234 + rank)
+    te_host = torch.randn(args.bs, 256, 768).pin_memory()
+    te_dev = te_host.to(device)
+    out_host = torch.empty(args.bs, 3, 64, 64).pin_memory()
+
+    def step_resident():
+        img = imagen.sample(text_embeds=te_dev, cond_scale=3., use_tqdm=False)
+        if world > 1:
+            img = all_gather_images(img, [args.bs] * world)
+        return img
+
+    def step_e2e():
+        te = te_host.to(device, non_blocking=True)          # H2D of this step's inputs from pinned memory
+        img = imagen.sample(text_embeds=te, cond_scale=3., use_tqdm=False)
+        if world > 1:
+            img = all_gather_images(img, [args.bs] * world)
+        out_host.copy_(img[rank * args.bs:(rank + 1) * args.bs] if world > 1 else img, non_blocking=True)   # D2H of the result
+        torch.cuda.current_stream(device).synchronize()
+        return img
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_resident()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    clocks = clk.summary()
+    launches = imagen.last_launch_count * args.steps
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    images = args.bs * world * args.steps
+    value = images / (ms / 1e3)
+    e2e_value = images / (ms_e2e / 1e3)
+    pk = peaks()
+    line = {
+        'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': te_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4},
+    }
+    if rank == 0:
+        R = 2 * args.bs
+        att_ms = time_attention_kernel(R, device)
+        att_tflops = ATTN_L0_GFLOP_PER_SAMPLE * R / 1e3 / (att_ms / 1e3)
+        line['roofline'] = {'kernel': 'flash_attn_kernel (multi-query self-attention, 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
+                            'bound': 'tensor', 'achieved': att_tflops, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': att_tflops / pk['tensor_burst'],
+                            'traffic': None, 'ms_per_launch': att_ms, 'algorithmic_gflop_per_launch': ATTN_L0_GFLOP_PER_SAMPLE * R,
+                            'peak_source': f"{pk['src']} burst bf16 (kernel timed alone)"}
+        step_tflop = GFLOP_PER_FORWARD_DIM128 * 2 * args.bs * args.timesteps / 1e3 if args.dim == 128 else None
+        if step_tflop:
+            ach = step_tflop / (ms / args.steps / 1e3)
+            line['whole_step'] = {'algorithmic_tflop_per_step': step_tflop, 'achieved_tflops': ach, 'frac_of_sustained_bf16': ach / pk['tensor_sustained']}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cpu_reference_step(args.dim, 1)
+            t = min(cpu_reference_step(args.dim, 1) for _ in range(2))
+            line['cpu_baseline'] = {'value': 1 / (t * args.timesteps), 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': f'1 of {args.timesteps} DDPM denoising steps (cond+null pass) at bs=1 through the oracle port, extrapolated x{args.timesteps}'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -98,8 +98,9 @@ __device__ float block_threshold(F absval, long long n, const Quant& q, unsigned
     v_hi = (count_le >= (unsigned)q.q_lo + 2u) ? v_lo : mn_f;
   }
   // torch.lerp(a, b, w): w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)
+  // (ATen's CUDA lerp kernel is compiled with FMA contraction, so the reference-on-GPU value is the fused one)
   const float diff = __fsub_rn(v_hi, v_lo);
-  float s = q.q_w < 0.5f ? __fadd_rn(v_lo, __fmul_rn(q.q_w, diff)) : __fsub_rn(v_hi, __fmul_rn(diff, __fsub_rn(1.f, q.q_w)));
+  float s = q.q_w < 0.5f ? __fmaf_rn(q.q_w, diff, v_lo) : __fmaf_rn(-diff, __fsub_rn(1.f, q.q_w), v_hi);
   return fmaxf(s, 1.f);
 }
 

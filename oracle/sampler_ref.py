@@ -72,14 +72,14 @@ def resize_nearest(img, size):                        # resize_image_to, imagen_
 
 def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, cond_scale=1.,
                        pred_objective='noise', dynamic_thresholding=True, percentile=0.95,
-                       unet_kwargs=None, lowres_log_snr=None, trace=None):
+                       unet_kwargs=None, lowres_log_snr=None, trace=None, randn=torch.randn):
     """Imagen.p_sample_loop (imagen_pytorch.py:2167-2289) + p_sample (:2112-2165) +
     p_mean_variance (:2042-2110), no inpainting / init image / self-cond.
     unet_fn(x, log_snr, cond_scale=..., **unet_kwargs) -> prediction."""
     unet_kwargs = dict(unet_kwargs or {})
     log_snr_fn = LOG_SNR[schedule]
     batch = shape[0]
-    img = torch.randn(shape)                                                   # :2195
+    img = randn(shape)                                                         # :2195
     for times, times_next in sampling_timesteps(timesteps, batch):             # :2242
         pred = unet_fn(img, log_snr_fn(times), cond_scale=cond_scale,
                        lowres_noise_times=lowres_log_snr, **unet_kwargs)       # :2072-2083
@@ -98,7 +98,7 @@ def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, con
         else:
             x_start = x_start.clamp(-1., 1.)
         mean, _, log_var = q_posterior(log_snr_fn, x_start, img, times, times_next)
-        noise = torch.randn_like(img)                                          # :2160
+        noise = randn(tuple(img.shape))                                        # :2160 (randn_like)
         nonzero = (1 - (times_next == 0).float()).view(batch, 1, 1, 1)
         img = mean + nonzero * (0.5 * log_var).exp() * noise                   # :2164
         if trace is not None:
@@ -109,7 +109,8 @@ def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, con
 
 def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps=1000, cond_scale=1.,
                   noise_schedules=('cosine',), lowres_sample_noise_level=0.2, dynamic_thresholding=True,
-                  pred_objectives='noise', stop_at_unet_number=None, return_all_unet_outputs=False, trace=None):
+                  pred_objectives='noise', stop_at_unet_number=None, return_all_unet_outputs=False, trace=None,
+                  randn=torch.randn):
     """Imagen.sample (imagen_pytorch.py:2291-2498), text_embeds path, no video/inpaint.
     unets: list of (state_dict, cfg)."""
     n = len(unets)
@@ -132,7 +133,7 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
             low = resize_nearest(img, size) * 2 - 1
             ls = beta_linear_log_snr(lt)
             a, s = log_snr_to_alpha_sigma(ls.view(-1, 1, 1, 1))
-            low = a * low + s * torch.randn_like(low)                          # q_sample :272-284
+            low = a * low + s * randn(tuple(low.shape))                        # q_sample :272-284 (randn_like)
             kw['lowres_cond_img'] = low
             lowres_log_snr = beta_linear_log_snr(lt)                           # :2081
         fn = lambda x, t, cond_scale, lowres_noise_times=None, _sd=sd, _cfg=cfg, **k: \
@@ -142,7 +143,7 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
                                  timesteps=timesteps[i], cond_scale=cond_scale[i],
                                  pred_objective=pred_objectives[i],
                                  dynamic_thresholding=dynamic_thresholding[i], unet_kwargs=kw,
-                                 lowres_log_snr=lowres_log_snr, trace=trace)
+                                 lowres_log_snr=lowres_log_snr, trace=trace, randn=randn)
         outputs.append(img)
         if stop_at_unet_number is not None and stop_at_unet_number == i + 1:
             break
@@ -178,17 +179,17 @@ def edm_precond_forward(unet_fn, x, sigma, *, sigma_data, dynamic_thresholding=T
 
 def edm_one_unet_sample(unet_fn, shape, *, num_sample_steps=32, sigma_min=0.002, sigma_max=80, sigma_data=0.5,
                         rho=7, S_churn=80, S_tmin=0.05, S_tmax=50, S_noise=1.003, cond_scale=1.,
-                        dynamic_thresholding=True, unet_kwargs=None, trace=None):
+                        dynamic_thresholding=True, unet_kwargs=None, trace=None, randn=torch.randn):
     """ElucidatedImagen.one_unet_sample, elucidated_imagen.py:392-545."""
     unet_kwargs = dict(unet_kwargs or {})
     sigmas = edm_sample_schedule(num_sample_steps, rho, sigma_min, sigma_max)
     gammas = torch.where((sigmas >= S_tmin) & (sigmas <= S_tmax),
                          min(S_churn / num_sample_steps, sqrt(2) - 1), 0.)
-    images = sigmas[0] * torch.randn(shape)                                    # :442
+    images = sigmas[0] * randn(shape)                                          # :442
     kw = dict(sigma_data=sigma_data, dynamic_thresholding=dynamic_thresholding, cond_scale=cond_scale, **unet_kwargs)
     for sigma, sigma_next, gamma in zip(sigmas[:-1], sigmas[1:], gammas[:-1]):
         sigma, sigma_next, gamma = (t.item() for t in (sigma, sigma_next, gamma))   # :484
-        eps = S_noise * torch.randn(shape)                                     # :489
+        eps = S_noise * randn(shape)                                           # :489
         sigma_hat = sigma + gamma * sigma
         images_hat = images + sqrt(sigma_hat ** 2 - sigma ** 2) * eps
         model_output = edm_precond_forward(unet_fn, images_hat, sigma_hat, **kw)
@@ -206,7 +207,7 @@ def edm_one_unet_sample(unet_fn, shape, *, num_sample_steps=32, sigma_min=0.002,
 
 
 def elucidated_sample(unets, image_sizes, *, text_embeds, text_masks=None, cond_scale=1.,
-                      lowres_sample_noise_level=0.2, dynamic_thresholding=True, hparams=None, trace=None):
+                      lowres_sample_noise_level=0.2, dynamic_thresholding=True, hparams=None, trace=None, randn=torch.randn):
     """ElucidatedImagen.sample (elucidated_imagen.py:547-751), text_embeds path."""
     n = len(unets)
     hparams = hparams or {}
@@ -221,11 +222,11 @@ def elucidated_sample(unets, image_sizes, *, text_embeds, text_masks=None, cond_
             lt = torch.full((batch,), lowres_sample_noise_level, dtype=torch.float32)
             low = resize_nearest(img, size) * 2 - 1
             a, s = log_snr_to_alpha_sigma(beta_linear_log_snr(lt).view(-1, 1, 1, 1))
-            kw['lowres_cond_img'] = a * low + s * torch.randn_like(low)
+            kw['lowres_cond_img'] = a * low + s * randn(tuple(low.shape))
             kw['lowres_noise_times'] = lt                                      # raw times, NOT log-snr (:700, passed through **kwargs :727-728)
         hp = {k: (unet_ref._tup(v, n)[i]) for k, v in hparams.items()}
         fn = lambda x, t, cond_scale, _sd=sd, _cfg=cfg, **k: \
             unet_ref.unet_forward_with_cond_scale(_sd, _cfg, x, t, cond_scale=cond_scale, **k)
         img = edm_one_unet_sample(fn, (batch, cfg['channels'], size, size), cond_scale=cond_scale[i],
-                                  dynamic_thresholding=dynamic_thresholding, unet_kwargs=kw, trace=trace, **hp)
+                                  dynamic_thresholding=dynamic_thresholding, unet_kwargs=kw, trace=trace, randn=randn, **hp)
     return img
