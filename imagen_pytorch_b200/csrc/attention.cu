@@ -220,14 +220,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attn_kernel(AttnParams p
 
 }  // namespace
 
+int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
+                      int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, float max_logit, cudaStream_t st);
+
 extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k,
-                              const void* v, int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, void* stream) {
+                              const void* v, int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads,
+                              float max_logit, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(q && o && k && v, "attention: null pointer");
   B200_REQUIRE(rows > 0 && n_keys > 0 && B > 0 && n_heads > 0, "attention: bad shape rows=%d keys=%d B=%d heads=%d", rows, n_keys, B, n_heads);
   B200_REQUIRE((q_rs & 7) == 0 && (kv_rs & 7) == 0 && kv_rs >= 64 && (q_hs & 7) == 0 && (q_bs & 7) == 0 && (kv_bs & 7) == 0 && (kv_hs & 7) == 0,
                "attention: strides must be multiples of 8 elements (16 bytes)");
   B200_REQUIRE(n_heads <= 65535 && B <= 65535, "attention: grid too large");
+  // A usable logit bound selects the tcgen05 kernel (no running max, no rescale); 2^(-2*bound) must stay far above
+  // fp32 underflow.  Without one (<= 0) or with a huge one, the online-softmax mma.sync kernel below is used.
+  if (max_logit > 0.f && max_logit <= 40.f)
+    return b200_attention_tc(q, o, q_bs, q_hs, q_rs, rows, k, v, kv_bs, kv_hs, kv_rs, n_keys, B, n_heads, max_logit, st);
   AttnParams p;
   p.q = reinterpret_cast<const __nv_bfloat16*>(q);
   p.o = reinterpret_cast<__nv_bfloat16*>(o);

@@ -1,0 +1,289 @@
+// tcgen05 flash attention for cosine-sim attention with a KNOWN logit bound (head dim 64).
+//
+// Cosine-sim attention makes the logits bounded: q and k are unit vectors times learned per-dim scales, so
+// |s| <= 8 * max_d|q_scale_d * k_scale_d| (Cauchy-Schwarz).  With that bound C (in log2 units; Q arrives
+// pre-multiplied by 8*log2e) the softmax needs NO running maximum:  P = exp2(S - C) in (0, 1], so the output
+// accumulator O in TMEM is never rescaled and a key tile costs exactly two MMAs + one exp2 per score.
+// The host only takes this path when C is small enough that 2^(-2C) stays far above fp32 underflow;
+// otherwise the online-softmax kernel in attention.cu is used.
+//
+// Per CTA: 128 query rows (= the 128 TMEM lanes) x all keys, in tiles of 128 keys.
+//   warp 0      TMA producer: Q tile once, then a 3-stage ring of {K tile, V tile} (128 keys x 64, 128B swizzle)
+//   warp 1      tcgen05.mma issuer:  S[j%2] = Q K_j^T  (128x128x64, fp32 in TMEM, double buffered) and
+//               O += P_j V_j (128x64x128; A = P_j from shared memory K-major, B = V_j MN-major)
+//   warps 2..5  softmax: thread = query row: tcgen05.ld S -> exp2 -> bf16 P written to shared memory in the
+//               128B-swizzled K-major layout the MMA reads (fence.proxy.async), row sums in registers;
+//               at the end O / l -> bf16 -> global.
+// S of tile j+1 is issued before the P V MMA of tile j, so the tensor pipe works on the next scores while the
+// softmax warps are busy with the current ones.
+//
+// Replaces the same reference arithmetic as attention.cu (Attention.forward / CrossAttention.forward einsum ->
+// softmax -> einsum, imagen_pytorch.py:565-588, :818-833).
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int FA_BM = 128;
+constexpr int FA_BN = 128;
+constexpr int FA_D = 64;
+constexpr int FA_STAGES = 3;
+constexpr int FA_THREADS = 192;
+constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
+constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
+constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
+constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;       // 32 KB (two 64-key K-major blocks)
+constexpr int FA_TMEM_COLS = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
+constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct FaParams {
+  __nv_bfloat16* o;
+  long long q_bs, q_hs;
+  int q_rs, rows, n_keys;
+  int q_heads_first, kv_heads_first;   // coordinate order of the (rows, heads) dims in the tensor maps
+  float max_logit;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + FA_Q_BYTES;
+  uint8_t* sP = sKV + FA_STAGES * FA_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+  uint64_t* q_full = bars;                       // [1]
+  uint64_t* kv_full = bars + 1;                  // [STAGES]
+  uint64_t* kv_empty = kv_full + FA_STAGES;      // [STAGES]
+  uint64_t* s_full = kv_empty + FA_STAGES;       // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* p_full = s_empty + 2;                // [2]
+  uint64_t* p_empty = p_full + 2;                // [2]
+  uint64_t* o_full = p_empty + 2;                // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * FA_BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);   // every softmax thread arrives after its last tcgen05.ld of the buffer
+      mbar_init(&p_full[s], 128);    // every softmax thread arrives after writing its P row
+      mbar_init(&p_empty[s], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      mbar_expect_tx(q_full, FA_Q_BYTES);
+      if (p.q_heads_first) tma_load_4d(sQ, &mapQ, q_full, 0, h, row0, b);
+      else tma_load_4d(sQ, &mapQ, q_full, 0, row0, h, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % FA_STAGES;
+        const uint32_t n = (uint32_t)(j / FA_STAGES);
+        mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
+        uint8_t* dst = sKV + st * FA_KV_BYTES;
+        if (p.kv_heads_first) {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+        } else {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      // S: M=128, N=128, A/B K-major.   PV: M=128, N=64, A K-major, B MN-major (bit 16).
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t tmem_o = tmem_base + 256;
+      auto issue_s = [&](int j) {
+        const int st = j % FA_STAGES, buf = j & 1;
+        mbar_wait(&kv_full[st], (uint32_t)((j / FA_STAGES) & 1));
+        mbar_wait(&s_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));   // softmax finished reading S[buf] (tile j-2)
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + st * FA_KV_BYTES);
+        const uint64_t adesc = make_sw128_kmajor_desc(q_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(k_addr);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(buf * FA_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[buf]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        const int st = j % FA_STAGES, buf = j & 1;
+        mbar_wait(&p_full[buf], (uint32_t)((j >> 1) & 1));         // softmax wrote P_j (and fenced it to the async proxy)
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + buf * FA_P_BYTES);
+        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) {
+          // A: P block (k/4) of 64 keys, 32 B per 16-key step inside the swizzled row; B: 16 key rows of V = 2 KB
+          const uint64_t adesc = make_sw128_kmajor_desc(p_addr + (uint32_t)((k >> 2) * (FA_BM * 128) + (k & 3) * 32));
+          const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)(k * 16 * 128), 1024, 1024);
+          umma_bf16(tmem_o, adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);   // K_j (read by the S MMA issued earlier) and V_j are free
+        umma_commit(&p_empty[buf]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ---------------- softmax / epilogue warps: thread = query row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float l = 0.f;
+    const float C = p.max_logit;
+    for (int j = 0; j < ntiles; ++j) {
+      const int buf = j & 1;
+      const uint32_t par = (uint32_t)((j >> 1) & 1);
+      mbar_wait(&s_full[buf], par);
+      tc_fence_after();
+      mbar_wait(&p_empty[buf], par ^ 1u);       // the P V MMA that read P[buf] two tiles ago has finished
+      uint8_t* prow = sP + buf * FA_P_BYTES + r * 128;
+      const int key0 = j * FA_BN;
+      const bool ragged = key0 + FA_BN > p.n_keys;
+#pragma unroll 1
+      for (int c = 0; c < FA_BN; c += 32) {
+        uint32_t sr[32];
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(buf * FA_BN + c), sr);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2_approx(__uint_as_float(sr[i]) - C);
+          float p1 = ex2_approx(__uint_as_float(sr[i + 1]) - C);
+          if (ragged) {
+            if (key0 + c + i >= p.n_keys) p0 = 0.f;
+            if (key0 + c + i + 1 >= p.n_keys) p1 = 0.f;
+          }
+          l += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        // keys [c, c+32) = 16-byte chunks (c%64)/8 .. +3 of the 64-key block c/64, XOR-swizzled by the row
+        uint8_t* blk = prow + (c >> 6) * (FA_BM * 128);
+        const int ch0 = (c & 63) >> 3;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          *reinterpret_cast<uint4*>(blk + (((ch0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      fence_proxy_async_smem();                 // make the generic-proxy P writes visible to the tensor-core (async) proxy
+      mbar_arrive(&p_full[buf]);
+    }
+    // ---- O / l -> global
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = row0 + r;
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs;
+#pragma unroll 1
+    for (int c = 0; c < FA_D; c += 32) {
+      uint32_t orr[32];
+      tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + c), orr);
+      tmem_ld_wait();
+      if (row < p.rows) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + 8 * t) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// 4-D map over [B][rows x heads][64]: dim0 = 64 head channels, dims 1/2 = (rows, heads) ordered by ascending stride
+// (heads_first: the 8 heads of a row are adjacent, as in the cross-attention q / k / v layout), dim3 = batch.
+int encode_rows_map(CUtensorMap* map, const void* base, int rows, int n_heads, int B, long long rs, long long hs, long long bs, int box_rows,
+                    bool heads_first, const char* what) {
+  EncodeTiledFn enc = get_encode_fn();
+  B200_REQUIRE(enc != nullptr, "attention: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4] = {(cuuint32_t)FA_D, 1, 1, 1};
+  dims[0] = FA_D;
+  if (heads_first) {
+    dims[1] = (cuuint64_t)n_heads; strides[0] = (cuuint64_t)hs * 2;
+    dims[2] = (cuuint64_t)rows;    strides[1] = (cuuint64_t)rs * 2;
+    box[2] = (cuuint32_t)box_rows;
+  } else {
+    dims[1] = (cuuint64_t)rows;    strides[0] = (cuuint64_t)rs * 2;
+    dims[2] = (cuuint64_t)n_heads; strides[1] = n_heads > 1 ? (cuuint64_t)hs * 2 : (cuuint64_t)rows * rs * 2;   // extent-1 dims still need a legal stride
+    box[1] = (cuuint32_t)box_rows;
+  }
+  dims[3] = (cuuint64_t)B;
+  strides[2] = B > 1 ? (cuuint64_t)bs * 2 : strides[1] * dims[2];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled(%s) failed with %d (rows=%d heads=%d B=%d rs=%lld hs=%lld bs=%lld)", what, (int)r,
+               rows, n_heads, B, rs, hs, bs);
+  return B200_OK;
+}
+
+}  // namespace
+
+// called by b200_attention (attention.cu) when the caller supplies a usable logit bound
+int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
+                      int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, float max_logit, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  int rc;
+  const bool q_hf = n_heads > 1 && q_hs < q_rs, kv_hf = n_heads > 1 && kv_hs < kv_rs;
+  if ((rc = encode_rows_map(&mq, q, rows, n_heads, B, q_rs, q_hs, q_bs, FA_BM, q_hf, "Q")) != B200_OK) return rc;
+  if ((rc = encode_rows_map(&mk, k, n_keys, n_heads, B, kv_rs, kv_hs, kv_bs, FA_BN, kv_hf, "K")) != B200_OK) return rc;
+  if ((rc = encode_rows_map(&mv, v, n_keys, n_heads, B, kv_rs, kv_hs, kv_bs, FA_BN, kv_hf, "V")) != B200_OK) return rc;
+  FaParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.q_bs = q_bs; p.q_hs = q_hs; p.q_rs = q_rs; p.rows = rows; p.n_keys = n_keys; p.max_logit = max_logit;
+  p.q_heads_first = q_hf ? 1 : 0; p.kv_heads_first = kv_hf ? 1 : 0;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    configured = true;
+  }
+  dim3 grid((rows + FA_BM - 1) / FA_BM, n_heads, B);
+  flash_attn_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mk, mv, p);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}

@@ -8,10 +8,18 @@ namespace {
 constexpr int ROW_THREADS = 256;
 constexpr int MAX_VPT = 16;  // 16-byte vectors cached per thread -> C <= 32*16*8 = 4096
 
+// threads per row: aim at ~2 vectors (32 B) per thread so every thread has two independent loads in flight,
+// while small rows still fill the warp
 int pick_tpr(int vecs) {
   int t = 1;
-  while (t * 2 <= vecs && t * 2 <= 32) t *= 2;
+  while (t * 4 <= vecs && t * 2 <= 32) t *= 2;
   return t;
+}
+int pick_vpt(int vecs, int tpr) {
+  const int need = (vecs + tpr - 1) / tpr;
+  int v = 1;
+  while (v < need) v *= 2;
+  return v;
 }
 
 template <int TPR>
@@ -34,7 +42,7 @@ struct RmsParams {
   long long M;
 };
 
-template <int TPR>
+template <int TPR, int VPT>
 __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParams p) {
   const int rows_per_block = ROW_THREADS / TPR;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
@@ -42,11 +50,11 @@ __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParam
   const int Ctot = p.C0 + p.C1;
   const int vecs = Ctot >> 3;
   const bool active = row < p.M;
-  uint4 buf[MAX_VPT];
+  uint4 buf[VPT];
   float ss = 0.f;
   if (active) {
 #pragma unroll
-    for (int i = 0; i < MAX_VPT; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = t + i * TPR;
       if (v < vecs) {
         const int c = v << 3;
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParam
   const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
   const float* film = p.film != nullptr ? p.film + (row / p.rows_per_sample) * (long long)p.film_ld : nullptr;
 #pragma unroll
-  for (int i = 0; i < MAX_VPT; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     const int v = t + i * TPR;
     if (v < vecs) {
       const int c = v << 3;
@@ -98,18 +106,18 @@ struct LnParams {
   long long M;
 };
 
-template <int TPR>
+template <int TPR, int VPT>
 __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
   const int rows_per_block = ROW_THREADS / TPR;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
   const int vecs = p.C >> 3;
   const bool active = row < p.M;
-  uint4 buf[MAX_VPT];
+  uint4 buf[VPT];
   float s = 0.f;
   if (active) {
 #pragma unroll
-    for (int i = 0; i < MAX_VPT; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = t + i * TPR;
       if (v < vecs) {
         buf[i] = __ldg(reinterpret_cast<const uint4*>(p.x + row * p.ldx + (v << 3)));
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
   float vs = 0.f;
   if (active) {
 #pragma unroll
-    for (int i = 0; i < MAX_VPT; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = t + i * TPR;
       if (v < vecs) {
         float f[8];
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
   if (!active) return;
   const float rstd = rsqrtf(vs / (float)p.C + p.eps);
 #pragma unroll
-  for (int i = 0; i < MAX_VPT; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     const int v = t + i * TPR;
     if (v < vecs) {
       const int c = v << 3;
@@ -236,44 +244,49 @@ __global__ void __launch_bounds__(GCA_WARPS * 32) gca_pool_kernel(const __nv_bfl
   }
 }
 
-__global__ void __launch_bounds__(256) gca_finish_kernel(const float* __restrict__ scratch, int nchunk, int C, int hidden,
-                                                         const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         const float* __restrict__ w2, const float* __restrict__ b2,
-                                                         float* __restrict__ gate) {
-  extern __shared__ float fsm[];  // pooled[C], hid[hidden]
-  float* pooled = fsm;
-  float* hid = fsm + C;
-  const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+// combine the per-chunk online-softmax partials -> pooled[b, c]
+__global__ void __launch_bounds__(256) gca_combine_kernel(const float* __restrict__ scratch, int nchunk, int C, float* __restrict__ pooled) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const float* sc = scratch + (long long)b * nchunk * (C + 2);
   float M = -INFINITY;
   for (int k = 0; k < nchunk; ++k) M = fmaxf(M, sc[(long long)k * (C + 2)]);
-  float L = 0.f;
+  float L = 0.f, a = 0.f;
   for (int k = 0; k < nchunk; ++k) {
     const float mk = sc[(long long)k * (C + 2)];
-    if (mk != -INFINITY) L += sc[(long long)k * (C + 2) + 1] * __expf(mk - M);
+    if (mk == -INFINITY) continue;
+    const float e = __expf(mk - M);
+    L += sc[(long long)k * (C + 2) + 1] * e;
+    if (c < C) a += sc[(long long)k * (C + 2) + 2 + c] * e;
   }
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int k = 0; k < nchunk; ++k) {
-      const float mk = sc[(long long)k * (C + 2)];
-      if (mk != -INFINITY) a += sc[(long long)k * (C + 2) + 2 + c] * __expf(mk - M);
+  if (c < C) pooled[(long long)b * C + c] = a / L;
+}
+
+// y[b, n0..n0+NW) = act(x[b, :] . W[n, :] + bias[n]) for ALL B rows at once: one warp per group of 2 output columns,
+// so each weight row is streamed exactly once (the net of GlobalContext is weight-read bound: B rows << C)
+template <int MAXB>
+__global__ void __launch_bounds__(256) gca_mlp_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                                      float* __restrict__ y, int B, int N, int K, int act) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  const float* wr = W + (long long)n * K;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __ldg(wr + k);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b)
+      if (b < B) acc[b] += w * __ldg(x + (long long)b * K + k);
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    const float s = warp_sum(acc[b]);
+    if (lane == 0 && b < B) {
+      const float v = s + bias[n];
+      y[(long long)b * N + n] = act == 1 ? silu_f(v) : sigmoid_f(v);
     }
-    pooled[c] = a / L;
-  }
-  __syncthreads();
-  for (int j = warp; j < hidden; j += nwarp) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += __ldg(w1 + (long long)j * C + c) * pooled[c];
-    s = warp_sum(s);
-    if (lane == 0) hid[j] = silu_f(s + b1[j]);
-  }
-  __syncthreads();
-  for (int c = warp; c < C; c += nwarp) {
-    float s = 0.f;
-    for (int j = lane; j < hidden; j += 32) s += __ldg(w2 + (long long)c * hidden + j) * hid[j];
-    s = warp_sum(s);
-    if (lane == 0) gate[(long long)b * C + c] = sigmoid_f(s + b2[c]);
   }
 }
 
@@ -373,14 +386,24 @@ __global__ void update_time_rows_kernel(const b200_timerow_job* __restrict__ job
 
 }  // namespace
 
-#define DISPATCH_TPR(tpr, KERNEL, grid_rows, ...)                                                       \
-  switch (tpr) {                                                                                         \
-    case 1: KERNEL<1><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 1), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
-    case 2: KERNEL<2><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 2), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
-    case 4: KERNEL<4><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 4), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
-    case 8: KERNEL<8><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 8), ROW_THREADS, 0, st>>>(__VA_ARGS__); break;   \
-    case 16: KERNEL<16><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 16), ROW_THREADS, 0, st>>>(__VA_ARGS__); break; \
-    default: KERNEL<32><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / 32), ROW_THREADS, 0, st>>>(__VA_ARGS__); break; \
+#define LAUNCH_ROW(T, V, KERNEL, grid_rows, ...) \
+  KERNEL<T, V><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / T), ROW_THREADS, 0, st>>>(__VA_ARGS__)
+#define DISPATCH_VPT(T, vpt, KERNEL, grid_rows, ...)                               \
+  switch (vpt) {                                                                   \
+    case 1: LAUNCH_ROW(T, 1, KERNEL, grid_rows, __VA_ARGS__); break;               \
+    case 2: LAUNCH_ROW(T, 2, KERNEL, grid_rows, __VA_ARGS__); break;               \
+    case 4: LAUNCH_ROW(T, 4, KERNEL, grid_rows, __VA_ARGS__); break;               \
+    case 8: LAUNCH_ROW(T, 8, KERNEL, grid_rows, __VA_ARGS__); break;               \
+    default: LAUNCH_ROW(T, 16, KERNEL, grid_rows, __VA_ARGS__); break;             \
+  }
+#define DISPATCH_TPR(tpr, vpt, KERNEL, grid_rows, ...)                             \
+  switch (tpr) {                                                                   \
+    case 1: DISPATCH_VPT(1, vpt, KERNEL, grid_rows, __VA_ARGS__); break;           \
+    case 2: DISPATCH_VPT(2, vpt, KERNEL, grid_rows, __VA_ARGS__); break;           \
+    case 4: DISPATCH_VPT(4, vpt, KERNEL, grid_rows, __VA_ARGS__); break;           \
+    case 8: DISPATCH_VPT(8, vpt, KERNEL, grid_rows, __VA_ARGS__); break;           \
+    case 16: DISPATCH_VPT(16, vpt, KERNEL, grid_rows, __VA_ARGS__); break;         \
+    default: DISPATCH_VPT(32, vpt, KERNEL, grid_rows, __VA_ARGS__); break;         \
   }
 
 extern "C" int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1_scale, const float* gamma_sqrtC, const float* film,
@@ -400,8 +423,9 @@ extern "C" int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1
                "rmsnorm: channel counts and strides must be multiples of 8 (C0=%d C1=%d)", p.C0, p.C1);
   const int vecs = Ctot >> 3;
   const int tpr = pick_tpr(vecs);
-  B200_REQUIRE((vecs + tpr - 1) / tpr <= MAX_VPT, "rmsnorm: C=%d too large", Ctot);
-  DISPATCH_TPR(tpr, rmsnorm_film_silu_kernel, M, p);
+  const int vpt = pick_vpt(vecs, tpr);
+  B200_REQUIRE(vpt <= MAX_VPT, "rmsnorm: C=%d too large", Ctot);
+  DISPATCH_TPR(tpr, vpt, rmsnorm_film_silu_kernel, M, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }
@@ -417,8 +441,9 @@ extern "C" int b200_layernorm(const void* x, int32_t ldx, const float* g, const 
   p.ldx = ldx; p.ldr = ldr; p.ldo = ldo; p.C = C; p.eps = eps; p.M = M;
   const int vecs = C >> 3;
   const int tpr = pick_tpr(vecs);
-  B200_REQUIRE((vecs + tpr - 1) / tpr <= MAX_VPT, "layernorm: C=%d too large", C);
-  DISPATCH_TPR(tpr, layernorm_kernel, M, p);
+  const int vpt = pick_vpt(vecs, tpr);
+  B200_REQUIRE(vpt <= MAX_VPT, "layernorm: C=%d too large", C);
+  DISPATCH_TPR(tpr, vpt, layernorm_kernel, M, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }
@@ -446,8 +471,16 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
   gca_pool_kernel<<<dim3(nchunk, B), GCA_WARPS * 32, smem1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, wk, bk,
                                                                    nchunk, scratch);
   B200_LAUNCH_OK();
-  const int smem2 = (C + hidden) * (int)sizeof(float);
-  gca_finish_kernel<<<B, 256, smem2, st>>>(scratch, nchunk, C, hidden, w1, b1, w2, b2, gate);
+  // scratch tail (after the B*nchunk*(C+2) partials): pooled [B, C] and hidden [B, hidden]
+  float* pooled = scratch + (long long)B * nchunk * (C + 2);
+  float* hid = pooled + (long long)B * C;
+  gca_combine_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(scratch, nchunk, C, pooled);
+  B200_LAUNCH_OK();
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int nb = B - b0 < 32 ? B - b0 : 32;
+    gca_mlp_kernel<32><<<(hidden * 32 + 255) / 256, 256, 0, st>>>(pooled + (long long)b0 * C, w1, b1, hid + (long long)b0 * hidden, nb, hidden, C, 1);
+    gca_mlp_kernel<32><<<(C * 32 + 255) / 256, 256, 0, st>>>(hid + (long long)b0 * hidden, w2, b2, gate + (long long)b0 * C, nb, C, hidden, 2);
+  }
   B200_LAUNCH_OK();
   return B200_OK;
 }

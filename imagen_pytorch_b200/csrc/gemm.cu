@@ -15,7 +15,7 @@
 // to isolate tensor-core/TMA descriptor bugs from epilogue/packing bugs.
 //
 // Reference arithmetic replaced: see include/b200_imagen.h (b200_conv_gemm).
-#include "common.cuh"
+#include "ptx.cuh"
 
 namespace {
 
@@ -43,102 +43,19 @@ struct GemmParams {
   int bw, bh, bb;
   int tiles_w, tiles_h;
   int N, Npad;
-  int nseg, total_chunks;
+  int nseg, total_chunks, ntiles_m;
   int nchunks[B200_MAX_SRC];
   SegDev seg[B200_MAX_SEG];
   EpiDev epi;
 };
-
-// ------------------------------------------------------------------------------------------ PTX wrappers
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline deadlock becomes an error, not a hang
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128B-swizzled operand tile (rows of 64 bf16 = 128 B; 8-row atoms 1024 B apart).
-// Field layout per cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;             // LBO: unused for swizzled K-major, canonical value 1
-  d |= (uint64_t)(1024 >> 4) << 32;   // SBO: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------ epilogue
 
 struct RowInfo {
   bool valid;
   int b, h, w;
-  long long row;  // (b*H + h)*W + w
+  long long row;   // (b*H + h)*W + w
+  long long orow;  // after the optional row remap
 };
 
 __device__ __forceinline__ RowInfo tile_row(const GemmParams& p, int tile, int m) {
@@ -152,97 +69,95 @@ __device__ __forceinline__ RowInfo tile_row(const GemmParams& p, int tile, int m
   r.b = bblk * p.bb + lb;
   r.valid = (r.w < p.W) && (r.h < p.H) && (r.b < p.B);
   r.row = ((long long)r.b * p.H + r.h) * p.W + r.w;
+  r.orow = r.row;
+  if (p.epi.rows_per_group > 0)
+    r.orow = (r.row / p.epi.rows_per_group) * (long long)p.epi.group_stride + p.epi.row_offset + (r.row % p.epi.rows_per_group);
   return r;
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == B200_ACT_SILU) return silu_f(x);
-  if (act == B200_ACT_GELU) return gelu_erf_f(x);
-  return x;
-}
-
-// One thread owns NC consecutive columns [col0, col0+NC) of one output row.
-template <int NC>
-__device__ __forceinline__ void epi_chunk(const GemmParams& p, const RowInfo& ri, int col0, float* v) {
-  const EpiDev& e = p.epi;
-  const int N = p.N;
+// bias + activation + scale on 16 consecutive columns starting at n (all branches are warp-uniform)
+__device__ __forceinline__ void epi_math16(const EpiDev& e, int n, float* v) {
+  if (e.bias != nullptr) {   // bias is padded to Npad by the caller: vector loads are always in bounds
 #pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    const int n = col0 + j;
-    float x = v[j];
-    if (e.bias != nullptr && n < N) x += __ldg(e.bias + n);
-    x = apply_act(x, e.act);
-    v[j] = x * e.out_scale;
-  }
-  if (NC == 64 && col0 < e.l2_cols) {
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < NC; ++j) ss += v[j] * v[j];
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-    for (int j = 0; j < NC; ++j) v[j] = v[j] * inv * (e.l2_scale != nullptr ? __ldg(e.l2_scale + j) : 1.f);
-  }
-  if (!ri.valid) return;
-  if (e.residual != nullptr) {
-    const __nv_bfloat16* rp = e.residual + ri.row * (long long)e.ldr + col0;
-#pragma unroll
-    for (int j = 0; j < NC; j += 8) {
-      if (col0 + j + 8 <= N && (e.ldr & 7) == 0) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) v[j + t] += f[t];
-      } else {
-        for (int t = 0; t < 8; ++t)
-          if (col0 + j + t < N) v[j + t] += __bfloat162float(rp[j + t]);
-      }
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
     }
   }
-  long long orow = ri.row;
-  if (e.rows_per_group > 0)
-    orow = (ri.row / e.rows_per_group) * (long long)e.group_stride + e.row_offset + (ri.row % e.rows_per_group);
+  if (e.act == B200_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+  } else if (e.act == B200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+  if (e.out_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= e.out_scale;
+  }
+}
 
+// residual + store of 16 consecutive columns [n, n+16) of one output row
+__device__ __forceinline__ void epi_store16(const GemmParams& p, const RowInfo& ri, int n, float* v) {
+  const EpiDev& e = p.epi;
+  const int N = p.N;
+  if (!ri.valid || n >= N) return;
+  const bool full = n + 16 <= N;
+  if (e.residual != nullptr) {
+    const __nv_bfloat16* rp = e.residual + ri.row * (long long)e.ldr + n;
+    if (full && (e.ldr & 7) == 0) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] += f[t];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp + 8)), f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[8 + t] += f[t];
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t)
+        if (n + t < N) v[t] += __bfloat162float(rp[t]);
+    }
+  }
   if (e.out_mode == B200_OUT_BF16) {
     __nv_bfloat16* base;
     int ld, c;
-    if (e.split_col > 0 && col0 >= e.split_col) {
-      base = reinterpret_cast<__nv_bfloat16*>(e.out2); ld = e.ldc2; c = col0 - e.split_col;
+    if (e.split_col > 0 && n >= e.split_col) {
+      base = reinterpret_cast<__nv_bfloat16*>(e.out2); ld = e.ldc2; c = n - e.split_col;
     } else {
-      base = reinterpret_cast<__nv_bfloat16*>(e.out); ld = e.ldc; c = col0;
+      base = reinterpret_cast<__nv_bfloat16*>(e.out); ld = e.ldc; c = n;
     }
-    for (int rep = 0; rep < (e.dup_rows > 0 ? 2 : 1); ++rep) {
-      __nv_bfloat16* dst = base + (orow + (long long)rep * e.dup_rows) * ld + c;
-      const bool vec_ok = ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const int reps = e.dup_rows > 0 ? 2 : 1;
+    for (int rep = 0; rep < reps; ++rep) {
+      __nv_bfloat16* dst = base + (ri.orow + (long long)rep * e.dup_rows) * ld + c;
+      if (full && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        reinterpret_cast<uint4*>(dst)[0] = pack8(v);
+        reinterpret_cast<uint4*>(dst)[1] = pack8(v + 8);
+      } else {
 #pragma unroll
-      for (int j = 0; j < NC; j += 8) {
-        if (vec_ok && col0 + j + 8 <= N) {
-          *reinterpret_cast<uint4*>(dst + j) = pack8(v + j);
-        } else {
-          for (int t = 0; t < 8; ++t)
-            if (col0 + j + t < N) dst[j + t] = __float2bfloat16(v[j + t]);
-        }
+        for (int t = 0; t < 16; ++t)
+          if (n + t < N) dst[t] = __float2bfloat16(v[t]);
       }
     }
   } else if (e.out_mode == B200_OUT_PIXEL_SHUFFLE) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
     const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
-    for (int j = 0; j < NC; j += 8) {
-      const int n = col0 + j;
-      if (n >= N) break;
-      const int r = n / e.ps_C, c = n - r * e.ps_C;
+    for (int g8 = 0; g8 < 16; g8 += 8) {
+      const int nn = n + g8;
+      if (nn >= N) break;
+      const int r = nn / e.ps_C, c = nn - r * e.ps_C;
       const long long prow = ((long long)ri.b * H2 + 2 * ri.h + (r >> 1)) * W2 + 2 * ri.w + (r & 1);
       __nv_bfloat16* dst = out + prow * e.ldc + c;
       if ((e.ps_C & 7) == 0 && (e.ldc & 7) == 0) {
-        *reinterpret_cast<uint4*>(dst) = pack8(v + j);
+        *reinterpret_cast<uint4*>(dst) = pack8(v + g8);
       } else {
         for (int t = 0; t < 8; ++t) {
-          const int nn = n + t;
-          if (nn < N) {
-            const int rr = nn / e.ps_C, cc = nn - rr * e.ps_C;
+          const int n2 = nn + t;
+          if (n2 < N) {
+            const int rr = n2 / e.ps_C, cc = n2 - rr * e.ps_C;
             const long long pr = ((long long)ri.b * H2 + 2 * ri.h + (rr >> 1)) * W2 + 2 * ri.w + (rr & 1);
-            out[pr * e.ldc + cc] = __float2bfloat16(v[j + t]);
+            out[pr * e.ldc + cc] = __float2bfloat16(v[g8 + t]);
           }
         }
       }
@@ -250,43 +165,92 @@ __device__ __forceinline__ void epi_chunk(const GemmParams& p, const RowInfo& ri
   } else if (e.out_mode == B200_OUT_F32_NCHW) {
     float* out = reinterpret_cast<float*>(e.out);
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      const int n = col0 + j;
-      if (n < N) out[(((long long)ri.b * N + n) * p.H + ri.h) * p.W + ri.w] = v[j];
-    }
+    for (int t = 0; t < 16; ++t)
+      if (n + t < N) out[(((long long)ri.b * N + n + t) * p.H + ri.h) * p.W + ri.w] = v[t];
   } else {  // B200_OUT_F32
     float* out = reinterpret_cast<float*>(e.out);
-    for (int rep = 0; rep < (e.dup_rows > 0 ? 2 : 1); ++rep) {
-      float* dst = out + (orow + (long long)rep * e.dup_rows) * e.ldc + col0;
+    const int reps = e.dup_rows > 0 ? 2 : 1;
+    for (int rep = 0; rep < reps; ++rep) {
+      float* dst = out + (ri.orow + (long long)rep * e.dup_rows) * e.ldc + n;
+      if (full && (e.ldc & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (col0 + j < N) dst[j] = v[j];
+        for (int t = 0; t < 16; t += 4) *reinterpret_cast<float4*>(dst + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (n + t < N) dst[t] = v[t];
+      }
+    }
+  }
+}
+
+// Epilogue of one accumulator row over columns [n0, n0 + BNW).  LOAD(c, v) fetches 16 fp32 accumulator columns
+// starting at tile column c.  The column loop is deliberately NOT unrolled: a fully unrolled 256-column epilogue
+// overflowed the instruction cache (ncu: stall_no_inst dominated round-1's first GEMM profile).
+template <int BNW, class Load>
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, const RowInfo& ri, int n0, Load load) {
+  const EpiDev& e = p.epi;
+  constexpr int GROUP = BNW >= 64 ? 64 : BNW;
+  float v[16];
+#pragma unroll 1
+  for (int g0 = 0; g0 < BNW; g0 += GROUP) {
+    if (n0 + g0 >= p.N) break;
+    float inv = 1.f;
+    const bool l2 = (GROUP == 64) && (n0 + g0 < e.l2_cols);
+    if (l2) {   // F.normalize over the 64-column head: first pass = sum of squares of the activated values
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 16) {
+        load(g0 + c, v);
+        epi_math16(e, n0 + g0 + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ss += v[j] * v[j];
+      }
+      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+#pragma unroll 1
+    for (int c = 0; c < GROUP; c += 16) {
+      load(g0 + c, v);
+      epi_math16(e, n0 + g0 + c, v);
+      if (l2) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + c + j));
+          v[j] *= inv * s4.x; v[j + 1] *= inv * s4.y; v[j + 2] *= inv * s4.z; v[j + 3] *= inv * s4.w;
+        }
+      }
+      epi_store16(p, ri, n0 + g0 + c, v);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 kernel
+// Persistent: one CTA per SM loops over output tiles; the smem operand ring (TMA -> MMA) runs straight across
+// tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of
+// tile i+1.
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr int EPI_NC = BN >= 64 ? 64 : 32;
+  constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two accumulator stages (power of two)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int n0 = blockIdx.y * BN;
+  const int n_tiles_n = p.Npad / BN;
+  const int total_tiles = p.ntiles_m * n_tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -298,12 +262,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tmem_slot, (uint32_t)TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -313,25 +279,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer
-      const int wblk = tile % p.tiles_w;
-      const int hblk = (tile / p.tiles_w) % p.tiles_h;
-      const int bblk = tile / (p.tiles_w * p.tiles_h);
-      const int w0 = wblk * p.bw, h0 = hblk * p.bh, b0 = bblk * p.bb;
       int stage = 0;
       uint32_t phase = 0;
-      int kc = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int src = p.seg[s].src;
-        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : (src == 2 ? &mapA2 : &mapA3));
-        const int dh = p.seg[s].dh, dw = p.seg[s].dw;
-        const int nch = p.nchunks[src];
-        for (int cc = 0; cc < nch; ++cc, ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sA = smem + stage * STAGE_BYTES;
-          tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
-          tma_load_2d(sA + A_TILE_BYTES, &mapB, &full_bar[stage], kc * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tile = t / n_tiles_n, n0 = (t % n_tiles_n) * BN;
+        const int wblk = tile % p.tiles_w;
+        const int hblk = (tile / p.tiles_w) % p.tiles_h;
+        const int bblk = tile / (p.tiles_w * p.tiles_h);
+        const int w0 = wblk * p.bw, h0 = hblk * p.bh, b0 = bblk * p.bb;
+        int kc = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int src = p.seg[s].src;
+          const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : (src == 2 ? &mapA2 : &mapA3));
+          const int dh = p.seg[s].dh, dw = p.seg[s].dw;
+          const int nch = p.nchunks[src];
+          for (int cc = 0; cc < nch; ++cc, ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            uint8_t* sA = smem + stage * STAGE_BYTES;
+            tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+            tma_load_2d(sA + A_TILE_BYTES, &mapB, &full_bar[stage], kc * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -340,45 +309,55 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       // ---------------- MMA issuer (InstrDescriptor: c_format F32 [4,6)=1, a/b BF16 [7,10)=[10,13)=1,
       // K-major both, N>>3 at [17,23), M>>4 at [24,29))
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kc = 0; kc < p.total_chunks; ++kc) {
-        mbar_wait(&full_bar[stage], phase);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        for (int kc = 0; kc < p.total_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
     }
   } else {
     // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const RowInfo ri = tile_row(p, tile, m);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    float v[EPI_NC];
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += EPI_NC) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      tmem_ld32(taddr, v);
-      if (EPI_NC == 64) tmem_ld32(taddr + 32, v + 32);
-      if (n0 + c0 < p.N) epi_chunk<EPI_NC>(p, ri, n0 + c0, v);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tile = t / n_tiles_n, n0 = (t % n_tiles_n) * BN;
+      const RowInfo ri = tile_row(p, tile, m);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      epilogue_row<BN>(p, ri, n0, [&](int c, float* v) { tmem_ld16(taddr + (uint32_t)c, v); });
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
   }
 }
 
@@ -416,10 +395,10 @@ __global__ void conv_gemm_ref_kernel(RefParams rs, GemmParams p, const __nv_bflo
   scratch[m * p.Npad + n] = acc;
 }
 
-template <int NC>
+template <int BNW>
 __global__ void conv_gemm_ref_epilogue_kernel(GemmParams p, const float* __restrict__ scratch) {
   const long long M = (long long)p.B * p.H * p.W;
-  const int chunks = p.Npad / NC;
+  const int chunks = p.Npad / BNW;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * chunks) return;
   const int ch = (int)(idx % chunks);
@@ -428,28 +407,17 @@ __global__ void conv_gemm_ref_epilogue_kernel(GemmParams p, const float* __restr
   ri.valid = true;
   ri.w = (int)(m % p.W); ri.h = (int)((m / p.W) % p.H); ri.b = (int)(m / ((long long)p.W * p.H));
   ri.row = m;
-  float v[NC];
-  for (int j = 0; j < NC; ++j) v[j] = scratch[m * p.Npad + ch * NC + j];
-  if (ch * NC < p.N) epi_chunk<NC>(p, ri, ch * NC, v);
+  ri.orow = m;
+  if (p.epi.rows_per_group > 0)
+    ri.orow = (m / p.epi.rows_per_group) * (long long)p.epi.group_stride + p.epi.row_offset + (m % p.epi.rows_per_group);
+  const float* src = scratch + m * p.Npad + ch * BNW;
+  epilogue_row<BNW>(p, ri, ch * BNW, [&](int c, float* v) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = src[c + j];
+  });
 }
 
 // ------------------------------------------------------------------------------------------ host side
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
 
 int next_pow2(int v) {
   int r = 1;
@@ -465,7 +433,8 @@ int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams
     B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ntiles, p.Npad / BN);
+  const long long total = (long long)ntiles * (p.Npad / BN);
+  const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
   conv_gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
   B200_LAUNCH_OK();
   return B200_OK;
@@ -518,6 +487,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   const long long ntiles_ll = (long long)p.tiles_w * p.tiles_h * tiles_b;
   B200_REQUIRE(ntiles_ll < (1ll << 31), "conv_gemm: too many tiles");
   const int ntiles = (int)ntiles_ll;
+  p.ntiles_m = ntiles;
   // epilogue
   EpiDev& e = p.epi;
   e.bias = epi->bias; e.residual = reinterpret_cast<const __nv_bfloat16*>(epi->residual);
@@ -549,7 +519,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
       const long long t2 = M * (p.Npad / 64);
       conv_gemm_ref_epilogue_kernel<64><<<(unsigned)ceil_div64(t2, 128), 128, 0, st>>>(p, reinterpret_cast<const float*>(f32_scratch));
     } else {
-      const long long t2 = M * (p.Npad / 32);
+      const long long t2 = M;
       conv_gemm_ref_epilogue_kernel<32><<<(unsigned)ceil_div64(t2, 128), 128, 0, st>>>(p, reinterpret_cast<const float*>(f32_scratch));
     }
     B200_LAUNCH_OK();
@@ -561,7 +531,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   B200_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled not available from the driver");
   int BN;
   if (p.Npad <= 64) BN = p.Npad;
-  else if (p.Npad % 256 == 0 && (long long)ntiles * (p.Npad / 256) >= 120) BN = 256;
+  else if (p.Npad % 256 == 0 && (long long)ntiles * (p.Npad / 256) >= sm_count()) BN = 256;   // wide tiles only if they still fill the chip
   else BN = 128;
   CUtensorMap maps[B200_MAX_SRC];
   memset(maps, 0, sizeof(maps));
@@ -589,10 +559,10 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (Ktot=%d Npad=%d BN=%d)", (int)r, Ktot, p.Npad, BN);
   }
   switch (BN) {
-    // stage counts sized so that two CTAs (BN <= 128) share one SM: one CTA's epilogue overlaps the other's mainloop
-    case 32: return launch_tc<32, 4>(maps, mapB, p, ntiles, st);
-    case 64: return launch_tc<64, 4>(maps, mapB, p, ntiles, st);
-    case 128: return launch_tc<128, 3>(maps, mapB, p, ntiles, st);
+    // persistent, one CTA per SM: the whole 227 KB of shared memory goes to the operand ring
+    case 32: return launch_tc<32, 8>(maps, mapB, p, ntiles, st);
+    case 64: return launch_tc<64, 8>(maps, mapB, p, ntiles, st);
+    case 128: return launch_tc<128, 6>(maps, mapB, p, ntiles, st);
     default: return launch_tc<256, 4>(maps, mapB, p, ntiles, st);
   }
 }

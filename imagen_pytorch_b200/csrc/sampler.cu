@@ -259,10 +259,10 @@ extern "C" int b200_ddpm_step(float* x, const float* pred, const float* noise, c
   B200_REQUIRE(!thresholding || (q_lo >= 0 && q_hi >= q_lo && q_hi <= q_lo + 1 && q_hi < chw), "ddpm_step: bad quantile ranks");
   Quant q{q_lo, q_hi, q_w, thresholding};
   const int smem = smp_smem(chw);
-  static int cfg = 0;
-  if (smem > 48 * 1024 && smem > cfg) {
+  static bool cfg = false;   // dynamic cache + 1.2 KB static histogram exceeds the 48 KB default already at 3x64x64
+  if (!cfg) {
     B200_CUDA_OK(cudaFuncSetAttribute(ddpm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_CACHE_FLOATS * 4));
-    cfg = SMP_CACHE_FLOATS * 4;
+    cfg = true;
   }
   ddpm_step_kernel<<<B, SMP_THREADS, smem, st>>>(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q);
   B200_LAUNCH_OK();
@@ -279,10 +279,10 @@ extern "C" int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, floa
   B200_REQUIRE(B > 0 && (R == B || R == 2 * B) && chw > 0, "edm_phase: bad R=%d B=%d", R, B);
   Quant q{q_lo, q_hi, q_w, thresholding};
   const int smem = phase == 0 ? 0 : smp_smem(chw);
-  static int cfg = 0;
-  if (smem > 48 * 1024 && smem > cfg) {
+  static bool cfg = false;
+  if (!cfg) {
     B200_CUDA_OK(cudaFuncSetAttribute(edm_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_CACHE_FLOATS * 4));
-    cfg = SMP_CACHE_FLOATS * 4;
+    cfg = true;
   }
   if (phase == 0) {
     // commit the step counter staged by the previous step's last phase (step_ctr[1]); step_ctr is int32[2]

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from functools import partial
 
 import torch
@@ -222,7 +223,7 @@ class UnetPlan:
         n, Cc = h.H * h.W, h.C
         hid = sd[p + '.net.0.weight'].shape[0]
         nchunk = self.lib.b200_gca_nchunk(n)
-        scratch = self._zeros((R, nchunk, Cc + 2), torch.float32)
+        scratch = self._zeros((R * nchunk * (Cc + 2) + R * Cc + R * hid,), torch.float32)
         gate = self._zeros((R, Cc), torch.float32)
         wk = self._f32(sd[p + '.to_k.weight'].flatten())
         w1 = self._f32(sd[p + '.net.0.weight'].reshape(hid, Cc))
@@ -232,6 +233,13 @@ class UnetPlan:
         self._add('b200_gca_gate', h.ptr, h.ld, R, n, Cc, wk.data_ptr(), float(sd[p + '.to_k.bias'].item()), w1.data_ptr(), b1.data_ptr(),
                   hid, w2.data_ptr(), b2.data_ptr(), scratch.data_ptr(), nchunk, gate.data_ptr())
         return gate
+
+    def _logit_bound(self, p):
+        """|q.k| <= 8 * max_d |q_scale_d * k_scale_d| for unit q, k (Cauchy-Schwarz), in log2 units, +2% for bf16 rounding.
+        The attention ABI takes the tcgen05 fixed-bound path when this is <= 40, else the online-softmax kernel."""
+        if os.environ.get('B200_IMAGEN_ATTN', 'tc') == 'mma':
+            return 0.0
+        return float((self.sd[p + '.q_scale'].abs() * self.sd[p + '.k_scale'].abs()).max().item()) * 8.0 * LOG2E * 1.02
 
     def _cross_attention(self, p, h: Rows, heads):
         """CrossAttention.forward + residual (imagen_pytorch.py:793-834, :749)."""
@@ -252,7 +260,8 @@ class UnetPlan:
         Kc[:, nk - 1, :] = (F.normalize(nkv[0], dim=-1) * sd[p + '.k_scale']).repeat(heads).to(BF16)
         Vc[:, nk - 1, :] = nkv[1].repeat(heads).to(BF16)
         o = self._new(M, inner, h.H, h.W)
-        self._add('b200_attention', q.ptr, o.ptr, n * inner, 64, inner, n, Kc.data_ptr(), Vc.data_ptr(), nk * inner, 64, inner, nk, R, heads)
+        self._add('b200_attention', q.ptr, o.ptr, n * inner, 64, inner, n, Kc.data_ptr(), Vc.data_ptr(), nk * inner, 64, inner, nk, R, heads,
+                  self._logit_bound(p))
         y = self._linear(o, sd[p + '.to_out.0.weight'], Cc)
         return self._layernorm(y, sd[p + '.to_out.1.g'], residual=h)
 
@@ -285,7 +294,8 @@ class UnetPlan:
             self.self_layers.append(layer)
             o = self._new(M, inner, x.H, x.W)
             # all heads of a sample share K/V: heads*n query rows of width 64 form ONE attention problem
-            self._add('b200_attention', q.ptr, o.ptr, n * inner, 0, 64, heads * n, Kb.data_ptr(), Vb.data_ptr(), Mtot * 64, 0, 64, Mtot, R, 1)
+            self._add('b200_attention', q.ptr, o.ptr, n * inner, 0, 64, heads * n, Kb.data_ptr(), Vb.data_ptr(), Mtot * 64, 0, 64, Mtot, R, 1,
+                      self._logit_bound(q_))
             y = self._linear(o, sd[q_ + '.to_out.0.weight'], Cc)
             x1 = self._layernorm(y, sd[q_ + '.to_out.1.g'], residual=x)
             f = self._layernorm(x1, sd[ff + '.0.g'])
@@ -419,7 +429,8 @@ class UnetPlan:
             max_elems = max(j.rows * j.width for j in self._jobs)
             ops.append((self.lib.b200_update_time_rows, (jb.data_ptr(), len(self._jobs), self.slots.data_ptr(), R, max_elems), 'b200_update_time_rows'))
         self._ops = ops + body
-        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate')   # gca = 2 kernels
+        # our kernel launches per U-Net evaluation (b200_gca_gate = pool + combine + 2 MLP kernels per 32 rows)
+        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * (1 + 2 * ((R + 31) // 32))
 
     # ------------------------------------------------------------------ execution
     def launch(self, stream=None):

@@ -128,10 +128,13 @@ int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* segs, int nse
  * (n_heads = 8, rows = n, q_row_stride = 512, per-head K/V).
  * problem (b, h): q + b*q_bs + h*q_hs (row stride q_rs), k/v + b*kv_bs + h*kv_hs (row stride kv_rs),
  * o like q.  Head dim = 64.  All strides in elements.
+ * max_logit: an upper bound of |q.k| in log2 units (8*log2e*max_d|q_scale_d*k_scale_d| for cosine-sim attention,
+ * by Cauchy-Schwarz).  0 < max_logit <= 40 selects the tcgen05 kernel (TMA -> tcgen05.mma S/P.V with TMEM
+ * accumulators, softmax without running max); <= 0 selects the online-softmax mma.sync kernel.
  * ------------------------------------------------------------------------------------------ */
 int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows,
                    const void* k, const void* v, int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys,
-                   int B, int n_heads, void* stream);
+                   int B, int n_heads, float max_logit, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row-wise normalisation kernels on pixel rows (HBM-bound).
@@ -152,7 +155,7 @@ int b200_layernorm(const void* x, int32_t ldx, const float* g, const float* beta
                    const void* residual, int32_t ldr, void* out, int32_t ldo, int64_t M, int32_t C, void* stream);
 
 /* GlobalContext (imagen_pytorch.py:945-970): gate[b, c] = sigmoid(W2 silu(W1 pool + b1) + b2),
- * pool[c] = sum_p softmax_p(x[p,:].wk + bk) x[p, c].  scratch: fp32 [B, nchunk, C + 2]. */
+ * pool[c] = sum_p softmax_p(x[p,:].wk + bk) x[p, c].  scratch: fp32 [B*nchunk*(C + 2) + B*C + B*hidden]. */
 int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C,
                   const float* wk, float bk, const float* w1, const float* b1, int32_t hidden,
                   const float* w2, const float* b2, float* scratch, int32_t nchunk, float* gate, void* stream);

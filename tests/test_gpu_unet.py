@@ -54,8 +54,8 @@ def test_unet_forward_matches_reference_golden(impl):
     out_cfg = u.forward_with_cond_scale(x, t, text_embeds=te, text_mask=tm, cond_scale=3.)
     e_c, e_n, e_g = rel_err(out, g['out_cond']), rel_err(out_null, g['out_null']), rel_err(out_cfg, g['out_cfg3'])
     record(f'unet_base_forward_impl{impl}', cond=e_c, null=e_n, cfg3=e_g, max_abs=(out.cpu() - g['out_cond']).abs().max())
-    # bf16 activations through ~150 layers of an untrained (non-contractive) net; measured ~1e-2, bound 4e-2
-    assert e_c < 4e-2 and e_n < 4e-2 and e_g < 6e-2
+    # bf16 activations through ~150 layers of an untrained (non-contractive) net; measured 1.2e-2 / 1.2e-2 / 1.4e-2 on B200
+    assert e_c < 3e-2 and e_n < 3e-2 and e_g < 4e-2
     assert (out - out_null).abs().max() > 0.1            # the conditioning path is live
 
 
@@ -66,7 +66,7 @@ def test_unet_sr_forward_matches_reference_golden():
             lowres_cond_img=g['lowres_cond_img'].to(DEV), lowres_noise_times=g['lowres_noise_times'].to(DEV))
     e = rel_err(out, g['out'])
     record('unet_sr_forward', rel=e)
-    assert e < 4e-2
+    assert e < 3e-2                                        # measured 8.1e-3
 
 
 def test_tcgen05_path_equals_simt_checker_on_the_whole_unet():
@@ -79,7 +79,8 @@ def test_tcgen05_path_equals_simt_checker_on_the_whole_unet():
     b = u(*args, **kw)
     e = rel_err(a, b)
     record('tcgen05_vs_simt_whole_unet', rel=e)
-    assert e < 1e-2                                        # same bf16 inputs everywhere; only fp32 accumulation order differs
+    # identical bf16 inputs; fp32 accumulation order differs, which flips bf16 roundings (2^-9) that then propagate: bf16-noise level
+    assert e < 3e-2
 
 
 # ------------------------------------------------------------------------------------------------ sampling trajectories vs oracle (same noise)
@@ -105,8 +106,8 @@ def test_ddpm_sample_matches_oracle_with_shared_noise():
     d = (out.cpu() - ref).abs()
     record('ddpm_sample_6steps', mean_abs=d.mean(), max_abs=d.max(), psnr=-10 * torch.log10((d ** 2).mean()))
     assert out.shape == ref.shape and out.min() >= 0 and out.max() <= 1
-    # images in [0,1] after 6 stochastic steps of an untrained net
-    assert d.mean() < 2e-2
+    # images in [0,1] after 6 stochastic steps of an untrained net; measured mean 2.0e-3, max 9.9e-3 (PSNR 51.6 dB)
+    assert d.mean() < 1e-2 and d.max() < 5e-2
 
 
 def test_ddpm_cascade_matches_oracle_with_shared_noise():
@@ -127,7 +128,7 @@ def test_ddpm_cascade_matches_oracle_with_shared_noise():
     d0, d1 = (outs[0].cpu() - refs[0]).abs(), (outs[1].cpu() - refs[1]).abs()
     record('ddpm_cascade', base_mean_abs=d0.mean(), sr_mean_abs=d1.mean(), sr_max_abs=d1.max())
     assert outs[1].shape == (2, 3, 32, 32)
-    assert d0.mean() < 2e-2 and d1.mean() < 3e-2
+    assert d0.mean() < 1e-2 and d1.mean() < 1e-2          # measured 2.3e-3 / 1.9e-3
 
 
 def test_elucidated_cascade_matches_oracle_with_shared_noise():
@@ -147,6 +148,7 @@ def test_elucidated_cascade_matches_oracle_with_shared_noise():
                                             hparams=dict(num_sample_steps=g['num_sample_steps']), randn=cuda_randn)
     d = (out.cpu() - ref).abs()
     record('edm_cascade', mean_abs=d.mean(), max_abs=d.max())
+    # sigma_max = 80: the first Heun steps run the untrained net on |x| ~ 80 inputs, which amplifies bf16 noise (measured mean 1.1e-2)
     assert d.mean() < 3e-2
 
 
@@ -162,7 +164,7 @@ def test_cuda_graph_replay_equals_eager_loop_bit_for_bit(monkeypatch):
     torch.manual_seed(5)
     b = im.sample(text_embeds=te, cond_scale=2., use_tqdm=False)
     assert torch.equal(a, b)
-    assert im.last_launch_count > 5 * 300                  # ~350 of our kernels per step
+    assert im.last_launch_count == 5 * (im.unets[0].plan(4, 2, 32, 32, 5).n_launches + 2)   # 263 U-Net kernels + randn copy + DDPM step, per step
 
 
 # ------------------------------------------------------------------------------------------------ properties at BASELINE.json shapes
