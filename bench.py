@@ -118,6 +118,19 @@ def time_attention_kernel(bs_rows, device, iters=10, max_logit=8 * 1.44269504088
     return e0.elapsed_time(e1) / iters
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on an
+    8-CPU quota thrashes: round 1 measured 50 s per step that way)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_step(dim, bs, threads=None):
     """One DDPM denoising step (cond + null U-Net pass, CFG combine, thresholded posterior update) of the reference
     algorithm on the host cores, through the oracle port.  Returns seconds."""
@@ -142,7 +155,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     bs = 1
     for _ in range(args.warmup):
@@ -264,7 +277,7 @@ def main():
             ach = step_tflop / (ms / args.steps / 1e3)
             line['whole_step'] = {'algorithmic_tflop_per_step': step_tflop, 'achieved_tflops': ach, 'frac_of_sustained_bf16': ach / pk['tensor_sustained']}
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             torch.set_num_threads(cores)
             cpu_reference_step(args.dim, 1)
             t = min(cpu_reference_step(args.dim, 1) for _ in range(2))

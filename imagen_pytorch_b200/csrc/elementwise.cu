@@ -168,79 +168,97 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
 
 // ---------------------------------------------------------------- GlobalContext
 
-constexpr int GCA_WARPS = 8;
-constexpr int GCA_MAX_VPL = 8;  // vectors of 8 channels per lane -> C <= 2048
-
-__global__ void __launch_bounds__(GCA_WARPS * 32) gca_pool_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows_per_sample,
-                                                                  int C, const float* __restrict__ wk, float bk, int nchunk,
-                                                                  float* __restrict__ scratch) {
-  extern __shared__ float gsm[];  // [GCA_WARPS][C + 2] then wk[C]
-  float* swk = gsm + GCA_WARPS * (C + 2);
-  const int chunk = blockIdx.x, b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) swk[c] = wk[c];
-  __syncthreads();
-  const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
-  const int p0 = chunk * ppc, p1 = min(rows_per_sample, p0 + ppc);
+// logit[row] = x[row, :] . wk + bk   (GlobalContext.to_k, a 1x1 conv to one channel)
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(ROW_THREADS) gca_logits_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, const float* __restrict__ wk,
+                                                                 float bk, float* __restrict__ logits, long long M) {
+  const int rows_per_block = ROW_THREADS / TPR;
+  const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
   const int vecs = C >> 3;
-  float acc[GCA_MAX_VPL][8];
+  float dot = 0.f;
+  if (row < M) {
 #pragma unroll
-  for (int i = 0; i < GCA_MAX_VPL; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int px = p0 + warp; px < p1; px += GCA_WARPS) {
-    const __nv_bfloat16* xr = x + ((long long)b * rows_per_sample + px) * ldx;
-    float f[GCA_MAX_VPL][8];
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < GCA_MAX_VPL; ++i) {
-      const int v = lane + i * 32;
+    for (int i = 0; i < VPT; ++i) {
+      const int v = t + i * TPR;
       if (v < vecs) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xr + (v << 3))), f[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dot += f[i][j] * swk[(v << 3) + j];
-      }
-    }
-    const float logit = warp_sum(dot) + bk;
-    const float m_new = fmaxf(m, logit);
-    const float sc = __expf(m - m_new), pw = __expf(logit - m_new);
-    m = m_new;
-    l = l * sc + pw;
-#pragma unroll
-    for (int i = 0; i < GCA_MAX_VPL; ++i) {
-      const int v = lane + i * 32;
-      if (v < vecs) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = acc[i][j] * sc + pw * f[i][j];
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + (v << 3))), f);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wk + (v << 3)));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wk + (v << 3) + 4));
+        dot += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
       }
     }
   }
-  float* mine = gsm + warp * (C + 2);
-  if (lane == 0) { mine[0] = m; mine[1] = l; }
-#pragma unroll
-  for (int i = 0; i < GCA_MAX_VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < vecs) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mine[2 + (v << 3) + j] = acc[i][j];
-    }
-  }
-  __syncthreads();
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < GCA_WARPS; ++w) M = fmaxf(M, gsm[w * (C + 2)]);
+  dot = group_sum<TPR>(dot);
+  if (row < M && t == 0) logits[row] = dot + bk;
+}
+
+constexpr int GCA_THREADS = 256;
+constexpr int GCA_MAX_CHUNK = 1024;   // pixels per chunk held in shared memory
+
+// softmax-weighted channel sums of one pixel chunk of one sample -> (max, sum, acc[C]) partial
+__global__ void __launch_bounds__(GCA_THREADS) gca_pool_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows_per_sample, int C,
+                                                               const float* __restrict__ logits, int nchunk, float* __restrict__ scratch) {
+  __shared__ float sw[GCA_MAX_CHUNK];
+  __shared__ float red[GCA_THREADS * 8];
+  __shared__ float sred[16];
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
+  const int p0 = chunk * ppc, np = max(0, min(rows_per_sample, p0 + ppc) - p0);
+  const float* lg = logits + (long long)b * rows_per_sample + p0;
   float* out = scratch + ((long long)b * nchunk + chunk) * (C + 2);
-  for (int c = threadIdx.x; c < C + 2; c += blockDim.x) {
-    if (c == 0) { out[0] = M; continue; }
-    float s = 0.f;
+  // chunk max
+  float m = -INFINITY;
+  for (int p = tid; p < np; p += GCA_THREADS) m = fmaxf(m, lg[p]);
+  m = warp_max(m);
+  if ((tid & 31) == 0) sred[tid >> 5] = m;
+  __syncthreads();
+  m = sred[0];
 #pragma unroll
-    for (int w = 0; w < GCA_WARPS; ++w) {
-      const float mw = gsm[w * (C + 2)];
-      const float e = (mw == -INFINITY) ? 0.f : __expf(mw - M);
-      s += gsm[w * (C + 2) + c] * e;
+  for (int w = 1; w < GCA_THREADS / 32; ++w) m = fmaxf(m, sred[w]);
+  __syncthreads();
+  // weights + their sum
+  float l = 0.f;
+  for (int p = tid; p < np; p += GCA_THREADS) {
+    const float e = __expf(lg[p] - m);
+    sw[p] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  if ((tid & 31) == 0) sred[8 + (tid >> 5)] = l;
+  __syncthreads();
+  // weighted channel sums: thread = (8-channel vector cv, pixel lane pl)
+  const int vecs = C >> 3;
+  const int npl = GCA_THREADS / vecs > 0 ? GCA_THREADS / vecs : 1;
+  const int cv = tid % vecs, pl = tid / vecs;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < npl && tid < npl * vecs) {
+    const __nv_bfloat16* xb = x + ((long long)b * rows_per_sample + p0) * ldx + (cv << 3);
+#pragma unroll 4
+    for (int p = pl; p < np; p += npl) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (long long)p * ldx)), f);
+      const float w = sw[p];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += w * f[j];
     }
-    out[c] = s;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[tid * 8 + j] = acc[j];
+  __syncthreads();
+  for (int c = tid; c < C; c += GCA_THREADS) {
+    const int v = c >> 3, j = c & 7;
+    float s = 0.f;
+    for (int q = 0; q < npl; ++q) s += red[(q * vecs + v) * 8 + j];
+    out[2 + c] = s;
+  }
+  if (tid == 0) {
+    float L = 0.f;
+#pragma unroll
+    for (int w = 0; w < GCA_THREADS / 32; ++w) L += sred[8 + w];
+    out[0] = np > 0 ? m : -INFINITY;
+    out[1] = L;
   }
 }
 
@@ -270,6 +288,10 @@ __global__ void __launch_bounds__(256) gca_mlp_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
+  const int b0 = blockIdx.y * MAXB;
+  x += (long long)b0 * K;
+  y += (long long)b0 * N;
+  B = B - b0 < MAXB ? B - b0 : MAXB;
   float acc[MAXB];
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
@@ -451,7 +473,7 @@ extern "C" int b200_layernorm(const void* x, int32_t ldx, const float* g, const 
 extern "C" int b200_gca_nchunk(int32_t rows_per_sample) {
   int n = rows_per_sample / 256;
   if (n < 1) n = 1;
-  if (n > 64) n = 64;
+  if (n > 4096) n = 4096;
   return n;
 }
 
@@ -460,27 +482,25 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
                              int32_t nchunk, float* gate, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(x && wk && w1 && b1 && w2 && b2 && scratch && gate, "gca: null pointer");
-  B200_REQUIRE((C & 7) == 0 && C <= 32 * 8 * GCA_MAX_VPL && (ldx & 7) == 0, "gca: C=%d unsupported", C);
+  B200_REQUIRE((C & 7) == 0 && C <= 2048 && (ldx & 7) == 0, "gca: C=%d unsupported", C);
   B200_REQUIRE(nchunk >= 1 && B >= 1 && B <= 65535, "gca: bad nchunk/B");
-  const int smem1 = (GCA_WARPS * (C + 2) + C) * (int)sizeof(float);
-  static int smem1_cfg = 0;
-  if (smem1 > 48 * 1024 && smem1 > smem1_cfg) {
-    B200_CUDA_OK(cudaFuncSetAttribute(gca_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    smem1_cfg = smem1;
-  }
-  gca_pool_kernel<<<dim3(nchunk, B), GCA_WARPS * 32, smem1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, wk, bk,
-                                                                   nchunk, scratch);
-  B200_LAUNCH_OK();
-  // scratch tail (after the B*nchunk*(C+2) partials): pooled [B, C] and hidden [B, hidden]
+  B200_REQUIRE((rows_per_sample + nchunk - 1) / nchunk <= GCA_MAX_CHUNK, "gca: chunk of %d pixels too large", (rows_per_sample + nchunk - 1) / nchunk);
+  // scratch layout: partials [B*nchunk*(C+2)] | pooled [B*C] | hidden [B*hidden] | logits [B*rows_per_sample]
   float* pooled = scratch + (long long)B * nchunk * (C + 2);
   float* hid = pooled + (long long)B * C;
+  float* logits = hid + (long long)B * hidden;
+  const long long M = (long long)B * rows_per_sample;
+  const int vecs = C >> 3;
+  const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
+  DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
+  B200_LAUNCH_OK();
+  gca_pool_kernel<<<dim3(nchunk, B), GCA_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, scratch);
+  B200_LAUNCH_OK();
   gca_combine_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(scratch, nchunk, C, pooled);
   B200_LAUNCH_OK();
-  for (int b0 = 0; b0 < B; b0 += 32) {
-    const int nb = B - b0 < 32 ? B - b0 : 32;
-    gca_mlp_kernel<32><<<(hidden * 32 + 255) / 256, 256, 0, st>>>(pooled + (long long)b0 * C, w1, b1, hid + (long long)b0 * hidden, nb, hidden, C, 1);
-    gca_mlp_kernel<32><<<(C * 32 + 255) / 256, 256, 0, st>>>(hid + (long long)b0 * hidden, w2, b2, gate + (long long)b0 * C, nb, C, hidden, 2);
-  }
+  const int bg = (B + 7) / 8;
+  gca_mlp_kernel<8><<<dim3((hidden * 32 + 255) / 256, bg), 256, 0, st>>>(pooled, w1, b1, hid, B, hidden, C, 1);
+  gca_mlp_kernel<8><<<dim3((C * 32 + 255) / 256, bg), 256, 0, st>>>(hid, w2, b2, gate, B, C, hidden, 2);
   B200_LAUNCH_OK();
   return B200_OK;
 }

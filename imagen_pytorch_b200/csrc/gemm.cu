@@ -184,45 +184,65 @@ __device__ __forceinline__ void epi_store16(const GemmParams& p, const RowInfo& 
   }
 }
 
-// Epilogue of one accumulator row over columns [n0, n0 + BNW).  LOAD(c, v) fetches 16 fp32 accumulator columns
-// starting at tile column c.  The column loop is deliberately NOT unrolled: a fully unrolled 256-column epilogue
-// overflowed the instruction cache (ncu: stall_no_inst dominated round-1's first GEMM profile).
-template <int BNW, class Load>
-__device__ __forceinline__ void epilogue_row(const GemmParams& p, const RowInfo& ri, int n0, Load load) {
+// bias/act/scale -> optional per-head L2 norm -> residual/store for GROUP (32 or 64) consecutive columns held in registers
+template <int GROUP>
+__device__ __forceinline__ void epi_group(const GemmParams& p, const RowInfo& ri, int n, float* v) {
   const EpiDev& e = p.epi;
-  constexpr int GROUP = BNW >= 64 ? 64 : BNW;
-  float v[16];
-#pragma unroll 1
-  for (int g0 = 0; g0 < BNW; g0 += GROUP) {
-    if (n0 + g0 >= p.N) break;
-    float inv = 1.f;
-    const bool l2 = (GROUP == 64) && (n0 + g0 < e.l2_cols);
-    if (l2) {   // F.normalize over the 64-column head: first pass = sum of squares of the activated values
-      float ss = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 16) {
-        load(g0 + c, v);
-        epi_math16(e, n0 + g0 + c, v);
+  if (n >= p.N) return;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) ss += v[j] * v[j];
-      }
-      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    }
-#pragma unroll 1
-    for (int c = 0; c < GROUP; c += 16) {
-      load(g0 + c, v);
-      epi_math16(e, n0 + g0 + c, v);
-      if (l2) {
+  for (int c = 0; c < GROUP; c += 16) epi_math16(e, n + c, v + c);
+  if (GROUP == 64 && n < e.l2_cols) {   // F.normalize over the 64-column head (thread-local: the thread owns the whole head)
+    float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + c + j));
-          v[j] *= inv * s4.x; v[j + 1] *= inv * s4.y; v[j + 2] *= inv * s4.z; v[j + 3] *= inv * s4.w;
-        }
-      }
-      epi_store16(p, ri, n0 + g0 + c, v);
+    for (int j = 0; j < GROUP; ++j) ss += v[j] * v[j];
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < GROUP; j += 4) {
+      float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + j));
+      v[j] *= inv * s4.x; v[j + 1] *= inv * s4.y; v[j + 2] *= inv * s4.z; v[j + 3] *= inv * s4.w;
     }
   }
+#pragma unroll
+  for (int c = 0; c < GROUP; c += 16) epi_store16(p, ri, n + c, v + c);
+}
+
+// Epilogue of one accumulator row over columns [n0, n0 + BNW).  load_async(c, v) starts fetching GROUP fp32 accumulator
+// columns from tile column c, wait() completes it.  Two register buffers: the TMEM read of group g+1 (~230 cycles of
+// tcgen05.ld latency) is in flight while group g is processed.  The group loop is NOT unrolled over the whole tile: a
+// fully unrolled 256-column epilogue overflowed the instruction cache (ncu: stall_no_inst dominated the first profile).
+template <int BNW, class LoadAsync, class Wait>
+__device__ __forceinline__ void epilogue_row(const GemmParams& p, const RowInfo& ri, int n0, LoadAsync load_async, Wait wait) {
+  constexpr int GROUP = BNW >= 64 ? 64 : BNW;
+  constexpr int NG = BNW / GROUP;
+  float va[GROUP], vb[GROUP];
+  load_async(0, va);
+  wait(va);
+#pragma unroll 1
+  for (int g = 0; g < NG; g += 2) {
+    if (g + 1 < NG) load_async((g + 1) * GROUP, vb);
+    epi_group<GROUP>(p, ri, n0 + g * GROUP, va);
+    if (g + 1 < NG) {
+      wait(vb);
+      if (g + 2 < NG) load_async((g + 2) * GROUP, va);
+      epi_group<GROUP>(p, ri, n0 + (g + 1) * GROUP, vb);
+      if (g + 2 < NG) wait(va);
+    }
+  }
+}
+
+// tcgen05.ld of N32*32 columns into v, completion deferred to tmem_wait_regs
+template <int N32>
+__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int i = 0; i < N32; ++i) tmem_ld32_nowait(taddr + 32 * i, reinterpret_cast<uint32_t*>(v) + 32 * i);
+}
+// wait::ld, then pin every destination register behind the wait so the compiler cannot hoist their uses above it
+template <int N>
+__device__ __forceinline__ void tmem_wait_regs(float* v) {
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 kernel
@@ -346,7 +366,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-      epilogue_row<BN>(p, ri, n0, [&](int c, float* v) { tmem_ld16(taddr + (uint32_t)c, v); });
+      constexpr int EG = BN >= 64 ? 64 : BN;
+      epilogue_row<BN>(p, ri, n0, [&](int c, float* v) { tmem_ld_async<EG / 32>(taddr + (uint32_t)c, v); },
+                       [&](float* v) { tmem_wait_regs<EG>(v); });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -411,10 +433,11 @@ __global__ void conv_gemm_ref_epilogue_kernel(GemmParams p, const float* __restr
   if (p.epi.rows_per_group > 0)
     ri.orow = (m / p.epi.rows_per_group) * (long long)p.epi.group_stride + p.epi.row_offset + (m % p.epi.rows_per_group);
   const float* src = scratch + m * p.Npad + ch * BNW;
+  constexpr int EG = BNW >= 64 ? 64 : BNW;
   epilogue_row<BNW>(p, ri, ch * BNW, [&](int c, float* v) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = src[c + j];
-  });
+    for (int j = 0; j < EG; ++j) v[j] = src[c + j];
+  }, [](float*) {});
 }
 
 // ------------------------------------------------------------------------------------------ host side

@@ -223,7 +223,7 @@ class UnetPlan:
         n, Cc = h.H * h.W, h.C
         hid = sd[p + '.net.0.weight'].shape[0]
         nchunk = self.lib.b200_gca_nchunk(n)
-        scratch = self._zeros((R * nchunk * (Cc + 2) + R * Cc + R * hid,), torch.float32)
+        scratch = self._zeros((R * nchunk * (Cc + 2) + R * Cc + R * hid + R * n,), torch.float32)
         gate = self._zeros((R, Cc), torch.float32)
         wk = self._f32(sd[p + '.to_k.weight'].flatten())
         w1 = self._f32(sd[p + '.net.0.weight'].reshape(hid, Cc))
@@ -429,8 +429,8 @@ class UnetPlan:
             max_elems = max(j.rows * j.width for j in self._jobs)
             ops.append((self.lib.b200_update_time_rows, (jb.data_ptr(), len(self._jobs), self.slots.data_ptr(), R, max_elems), 'b200_update_time_rows'))
         self._ops = ops + body
-        # our kernel launches per U-Net evaluation (b200_gca_gate = pool + combine + 2 MLP kernels per 32 rows)
-        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * (1 + 2 * ((R + 31) // 32))
+        # our kernel launches per U-Net evaluation (b200_gca_gate = logits + pool + combine + 2 MLP kernels)
+        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4
 
     # ------------------------------------------------------------------ execution
     def launch(self, stream=None):

@@ -155,7 +155,8 @@ int b200_layernorm(const void* x, int32_t ldx, const float* g, const float* beta
                    const void* residual, int32_t ldr, void* out, int32_t ldo, int64_t M, int32_t C, void* stream);
 
 /* GlobalContext (imagen_pytorch.py:945-970): gate[b, c] = sigmoid(W2 silu(W1 pool + b1) + b2),
- * pool[c] = sum_p softmax_p(x[p,:].wk + bk) x[p, c].  scratch: fp32 [B*nchunk*(C + 2) + B*C + B*hidden]. */
+ * pool[c] = sum_p softmax_p(x[p,:].wk + bk) x[p, c].  scratch: fp32 [B*nchunk*(C + 2) + B*C + B*hidden + B*rows_per_sample]
+ * (softmax partials | pooled | hidden | per-pixel logits). */
 int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C,
                   const float* wk, float bk, const float* w1, const float* b1, int32_t hidden,
                   const float* w2, const float* b2, float* scratch, int32_t nchunk, float* gate, void* stream);

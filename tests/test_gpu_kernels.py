@@ -267,7 +267,7 @@ def test_global_context_gate_and_gate_residual(n, Cc):
     w1, b1 = rnd(hid, Cc, scale=1 / math.sqrt(Cc), seed=2), rnd(hid, scale=0.1, seed=3)
     w2, b2 = rnd(Cc, hid, scale=1 / math.sqrt(hid), seed=4), rnd(Cc, scale=0.1, seed=5)
     nchunk = _lib.load().b200_gca_nchunk(n)
-    scratch = torch.zeros(B * nchunk * (Cc + 2) + B * Cc + B * hid, device=DEV)
+    scratch = torch.zeros(B * nchunk * (Cc + 2) + B * Cc + B * hid + B * n, device=DEV)
     gate = torch.zeros(B, Cc, device=DEV)
     _lib.call('b200_gca_gate', x.data_ptr(), Cc, B, n, Cc, wk.data_ptr(), bk, w1.data_ptr(), b1.data_ptr(), hid, w2.data_ptr(), b2.data_ptr(),
               scratch.data_ptr(), nchunk, gate.data_ptr(), stream())
