@@ -131,29 +131,46 @@ def usable_cores():
     return n
 
 
-def cpu_reference_step(dim, bs, threads=None):
-    """One DDPM denoising step (cond + null U-Net pass, CFG combine, thresholded posterior update) of the reference
-    algorithm on the host cores, through the oracle port.  Returns seconds."""
+def cpu_reference_step(dim, bs, threads=None, device='cpu', steps=1):
+    """`steps` DDPM denoising steps (cond + null U-Net pass, CFG combine, thresholded posterior update) of the reference
+    algorithm through the oracle port: on the host cores (device='cpu', the baseline), or -- informational only, flag
+    --eager-gpu -- the same eager fp32 PyTorch ops on the GPU (the "PyTorch-eager on B200" denominator of the north star).
+    Returns seconds per step."""
     from oracle import unet_ref, sampler_ref
     import imagen_pytorch_b200 as b2
     if threads:
         torch.set_num_threads(threads)
     torch.manual_seed(0)
     u = b2.Unet(dim=dim)
-    sd = {k: v.detach().clone() for k, v in u.state_dict().items()}
+    sd = {k: v.detach().clone().to(device) for k, v in u.state_dict().items()}
     sd['final_conv.weight'].normal_(0, 0.02)
     cfg = unet_ref.unet_config(dim=dim)
-    te = torch.randn(bs, 256, 768)
+    te = torch.randn(bs, 256, 768, device=device)
     fn = lambda x, t, cond_scale, lowres_noise_times=None, **k: unet_ref.unet_forward_with_cond_scale(sd, cfg, x, t, cond_scale=cond_scale, **k)
+    randn = (lambda s: torch.randn(tuple(s), device=device))
+    kw = dict(text_embeds=te, text_mask=torch.ones(bs, 256, dtype=torch.bool, device=device))
+    if device != 'cpu':
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.no_grad():
-        sampler_ref.ddpm_p_sample_loop(fn, (bs, 3, 64, 64), timesteps=1, cond_scale=3., unet_kwargs=dict(text_embeds=te, text_mask=torch.ones(bs, 256, dtype=torch.bool)))
-    return time.perf_counter() - t0
+        sampler_ref.ddpm_p_sample_loop(fn, (bs, 3, 64, 64), timesteps=steps, cond_scale=3., unet_kwargs=kw, randn=randn)
+    if device != 'cpu':
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
+        return
+    if args.eager_gpu:
+        # informational: the reference's algorithm as eager fp32 PyTorch ops on this GPU (cuDNN TF32 convs, cuBLAS fp32 bmm,
+        # materialised N x M attention scores), full batch, a few denoising steps extrapolated to the schedule length
+        cpu_reference_step(args.dim, args.bs, device='cuda', steps=2)
+        dt = cpu_reference_step(args.dim, args.bs, device='cuda', steps=max(2, args.steps))
+        print(json.dumps({'impl': 'reference-eager-gpu', 'metric': 'images/sec', 'value': args.bs / (dt * args.timesteps), 'unit': 'images/s',
+                          'ms_per_denoising_step': dt * 1e3, 'dtype': 'f32 (TF32 conv)', 'config': workload_config(args),
+                          'note': 'oracle port executed with torch CUDA ops; not the product path, not the CPU baseline'}))
         return
     cores = usable_cores()
     torch.set_num_threads(cores)
@@ -192,6 +209,7 @@ def main():
     ap.add_argument('--dim', type=int, default=128)
     ap.add_argument('--timesteps', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager-gpu', action='store_true', help='with --impl reference: run the oracle port with torch CUDA ops (informational)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

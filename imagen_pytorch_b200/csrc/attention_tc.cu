@@ -11,7 +11,7 @@
 //   warp 0      TMA producer: Q tile once, then a 3-stage ring of {K tile, V tile} (128 keys x 64, 128B swizzle)
 //   warp 1      tcgen05.mma issuer:  S[j%2] = Q K_j^T  (128x128x64, fp32 in TMEM, double buffered) and
 //               O += P_j V_j (128x64x128; A = P_j from shared memory K-major, B = V_j MN-major)
-//   warps 2..9  softmax: thread = (query row, 64-key half): tcgen05.ld S -> exp2 -> bf16 P written to shared memory in the
+//   warps 2..17 softmax: thread = (query row, 32-key slice): tcgen05.ld S -> exp2 -> bf16 P written to shared memory in the
 //               128B-swizzled K-major layout the MMA reads (fence.proxy.async), row sums in registers;
 //               at the end O / l -> bf16 -> global.
 // S of tile j+1 is issued before the P V MMA of tile j, so the tensor pipe works on the next scores while the
@@ -27,13 +27,14 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_THREADS = 320;                    // TMA warp, MMA warp, 8 softmax warps
+constexpr int FA_SM_WARPS = 16;                    // softmax warps: 4 per scheduler sub-partition
+constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;  // + TMA warp + MMA warp
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;       // 32 KB (two 64-key K-major blocks)
 constexpr int FA_TMEM_COLS = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
-constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256 + 1024;   // + row-sum exchange
+constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256 + 2048;   // + row-sum exchange
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -67,7 +68,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* p_empty = p_full + 2;                // [2]
   uint64_t* o_full = p_empty + 2;                // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* sL = reinterpret_cast<float*>(bars + 32);   // [2][128] partial row sums of the two column halves
+  float* sL = reinterpret_cast<float*>(bars + 32);   // [4][128] partial row sums of the four 32-key column slices
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * FA_BM;
@@ -82,8 +83,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 256);   // every softmax thread arrives after its last tcgen05.ld of the buffer
-      mbar_init(&p_full[s], 256);    // every softmax thread arrives after writing its half P row
+      mbar_init(&s_empty[s], 32 * FA_SM_WARPS);   // every softmax thread arrives after its tcgen05.ld of the buffer
+      mbar_init(&p_full[s], 32 * FA_SM_WARPS);    // every softmax thread arrives after writing its slice of the P row
       mbar_init(&p_empty[s], 1);
     }
     mbar_init(o_full, 1);
@@ -159,39 +160,47 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       umma_commit(o_full);
     }
   } else {
-    // ---------------- softmax / epilogue warps 2..9: thread = (query row, 64-key half).  Two warps per scheduler
-    // sub-partition so MUFU / FMA / LSU work of one overlaps the TMEM-load latency of the other.
+    // ---------------- softmax / epilogue warps 2..17: thread = (query row, 32-key slice of every key tile).
+    // Four warps per scheduler sub-partition, and the TMEM read of tile j+1 is in flight while tile j is exponentiated,
+    // so the MUFU pipe (the real bound of head-dim-64 attention: 4*64 MMA flops per exp) stays busy.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // keys [64*half, 64*half + 64) of every tile
+    const int slice = (warp - 2) >> 2;      // keys [32*slice, 32*slice + 32) of every tile
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float l = 0.f;
     const float C = p.max_logit;
+    uint32_t cur[32], nxt[32];
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(slice * 32), cur);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(cur[i]));   // pin the destination registers behind the wait
+    tc_fence_before();
+    mbar_arrive(&s_empty[0]);
     for (int j = 0; j < ntiles; ++j) {
       const int buf = j & 1;
       const uint32_t par = (uint32_t)((j >> 1) & 1);
-      mbar_wait(&s_full[buf], par);
-      tc_fence_after();
-      uint32_t sr[64];
-      const uint32_t taddr = tmem_base + lane_off + (uint32_t)(buf * FA_BN + half * 64);
-      tmem_ld32_nowait(taddr, sr);
-      tmem_ld32_nowait(taddr + 32, sr + 32);
-      mbar_wait(&p_empty[buf], par ^ 1u);       // the P V MMA that read P[buf] two tiles ago has finished (overlaps the TMEM load)
-      tmem_ld_wait();
+      const bool more = j + 1 < ntiles;
+      if (more) {                               // start reading S_{j+1} (issued by the MMA warp one tile ahead)
+        const int nb = (j + 1) & 1;
+        mbar_wait(&s_full[nb], (uint32_t)(((j + 1) >> 1) & 1));
+        tc_fence_after();
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(nb * FA_BN + slice * 32), nxt);
+      }
+      mbar_wait(&p_empty[buf], par ^ 1u);       // the P V MMA that read P[buf] two tiles ago has finished
+      const int key0 = j * FA_BN + slice * 32;
+      const bool ragged = key0 + 32 > p.n_keys;
+      // this thread's 64 bytes of the P row: chunks 4*(slice&1) .. +3 of the 64-key block slice>>1
+      uint8_t* prow = sP + buf * FA_P_BYTES + (slice >> 1) * (FA_BM * 128) + r * 128;
+      const int ch0 = (slice & 1) * 4;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
-      tc_fence_before();
-      mbar_arrive(&s_empty[buf]);               // S[buf] is in registers: the tensor pipe may overwrite it with tile j+2
-      const int key0 = j * FA_BN + half * 64;
-      const bool ragged = key0 + 64 > p.n_keys;
-      uint8_t* prow = sP + buf * FA_P_BYTES + half * (FA_BM * 128) + r * 128;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < 4; ++t) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
-          float p1 = ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
+          float p0 = ex2_approx(__uint_as_float(cur[8 * t + i]) - C);
+          float p1 = ex2_approx(__uint_as_float(cur[8 * t + i + 1]) - C);
           if (ragged) {
             if (key0 + 8 * t + i >= p.n_keys) p0 = 0.f;
             if (key0 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
@@ -199,28 +208,37 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           l += p0 + p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        // 16-byte chunk t of this row's 64-key block, XOR-swizzled by the row (the layout TMA / UMMA use for SWIZZLE_128B)
-        *reinterpret_cast<uint4*>(prow + ((t ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        // 16-byte chunk of the row, XOR-swizzled by the row (the layout TMA / UMMA use for SWIZZLE_128B)
+        *reinterpret_cast<uint4*>(prow + (((ch0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();                 // make the generic-proxy P writes visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[buf]);
+      if (more) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(nxt[i]));
+        tc_fence_before();
+        mbar_arrive(&s_empty[(j + 1) & 1]);     // S_{j+1} is in registers: the tensor pipe may overwrite the buffer with tile j+3
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+      }
     }
-    // ---- O / l -> global: each half stores 32 of the 64 output channels
-    sL[half * FA_BM + r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // softmax warps only
-    const float inv = 1.f / (sL[r] + sL[FA_BM + r]);
+    // ---- O / l -> global: each slice stores 16 of the 64 output channels
+    sL[slice * FA_BM + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * FA_SM_WARPS) : "memory");   // softmax warps only
+    const float inv = 1.f / (sL[r] + sL[FA_BM + r] + sL[2 * FA_BM + r] + sL[3 * FA_BM + r]);
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int row = row0 + r;
-    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + half * 32;
-    uint32_t orr[32];
-    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + half * 32), orr);
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + slice * 16;
+    uint32_t orr[16];
+    tmem_ld16_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * 16), orr);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(orr[i]));
+    for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(orr[i]));
     if (row < p.rows) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 2; ++t) {
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
         u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);

@@ -97,11 +97,30 @@ __device__ __forceinline__ void epi_math16(const EpiDev& e, int n, float* v) {
   }
 }
 
-// residual + store of 16 consecutive columns [n, n+16) of one output row
+// residual + store of 16 consecutive columns [n, n+16) of one output row.
+// SIMPLE = plain bf16 row-major output, N % 16 == 0, 16-byte aligned rows, no split / remap / dup: the common case gets
+// its own tiny instruction stream (the epilogue is instruction-fetch sensitive, see epilogue_row).
+template <bool SIMPLE>
 __device__ __forceinline__ void epi_store16(const GemmParams& p, const RowInfo& ri, int n, float* v) {
   const EpiDev& e = p.epi;
   const int N = p.N;
   if (!ri.valid || n >= N) return;
+  if (SIMPLE) {
+    if (e.residual != nullptr) {
+      const __nv_bfloat16* rp = e.residual + ri.row * (long long)e.ldr + n;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] += f[t];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp + 8)), f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[8 + t] += f[t];
+    }
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + ri.row * (long long)e.ldc + n;
+    reinterpret_cast<uint4*>(dst)[0] = pack8(v);
+    reinterpret_cast<uint4*>(dst)[1] = pack8(v + 8);
+    return;
+  }
   const bool full = n + 16 <= N;
   if (e.residual != nullptr) {
     const __nv_bfloat16* rp = e.residual + ri.row * (long long)e.ldr + n;
@@ -184,65 +203,65 @@ __device__ __forceinline__ void epi_store16(const GemmParams& p, const RowInfo& 
   }
 }
 
-// bias/act/scale -> optional per-head L2 norm -> residual/store for GROUP (32 or 64) consecutive columns held in registers
-template <int GROUP>
-__device__ __forceinline__ void epi_group(const GemmParams& p, const RowInfo& ri, int n, float* v) {
-  const EpiDev& e = p.epi;
-  if (n >= p.N) return;
-#pragma unroll
-  for (int c = 0; c < GROUP; c += 16) epi_math16(e, n + c, v + c);
-  if (GROUP == 64 && n < e.l2_cols) {   // F.normalize over the 64-column head (thread-local: the thread owns the whole head)
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < GROUP; ++j) ss += v[j] * v[j];
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-    for (int j = 0; j < GROUP; j += 4) {
-      float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + j));
-      v[j] *= inv * s4.x; v[j + 1] *= inv * s4.y; v[j + 2] *= inv * s4.z; v[j + 3] *= inv * s4.w;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < GROUP; c += 16) epi_store16(p, ri, n + c, v + c);
-}
-
-// Epilogue of one accumulator row over columns [n0, n0 + BNW).  load_async(c, v) starts fetching GROUP fp32 accumulator
-// columns from tile column c, wait() completes it.  Two register buffers: the TMEM read of group g+1 (~230 cycles of
-// tcgen05.ld latency) is in flight while group g is processed.  The group loop is NOT unrolled over the whole tile: a
-// fully unrolled 256-column epilogue overflowed the instruction cache (ncu: stall_no_inst dominated the first profile).
-template <int BNW, class LoadAsync, class Wait>
+// Epilogue of one accumulator row over columns [n0, n0 + BNW) in chunks of 16 columns.
+// load_async(c, v) starts fetching 16 fp32 accumulator columns from tile column c; wait(v) completes it.
+// Design notes (both learnt from ncu on B200):
+//  * the loop body is deliberately small (one 16-column chunk) and NOT unrolled: only four warps run the epilogue, so it
+//    is instruction-fetch bound as soon as the body outgrows the L0 instruction cache (stall_no_inst dominated both a
+//    256-column and a 64-column unrolled version);
+//  * the TMEM read of chunk c+1 (~230 cycles of tcgen05.ld latency) is issued before chunk c is processed.
+template <int BNW, bool SIMPLE, class LoadAsync, class Wait>
 __device__ __forceinline__ void epilogue_row(const GemmParams& p, const RowInfo& ri, int n0, LoadAsync load_async, Wait wait) {
+  const EpiDev& e = p.epi;
   constexpr int GROUP = BNW >= 64 ? 64 : BNW;
-  constexpr int NG = BNW / GROUP;
-  float va[GROUP], vb[GROUP];
-  load_async(0, va);
-  wait(va);
+  constexpr int NCH = GROUP / 16;
+  float v[16], vn[16];
 #pragma unroll 1
-  for (int g = 0; g < NG; g += 2) {
-    if (g + 1 < NG) load_async((g + 1) * GROUP, vb);
-    epi_group<GROUP>(p, ri, n0 + g * GROUP, va);
-    if (g + 1 < NG) {
-      wait(vb);
-      if (g + 2 < NG) load_async((g + 2) * GROUP, va);
-      epi_group<GROUP>(p, ri, n0 + (g + 1) * GROUP, vb);
-      if (g + 2 < NG) wait(va);
+  for (int g0 = 0; g0 < BNW; g0 += GROUP) {
+    if (n0 + g0 >= p.N) break;
+    float inv = 1.f;
+    const bool l2 = !SIMPLE && (GROUP == 64) && (n0 + g0 < e.l2_cols);
+    if (l2) {   // F.normalize over the 64-column head: first pass = sum of squares of the activated values
+      float ss = 0.f;
+      load_async(g0, v);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        wait(v);
+        if (c + 1 < NCH) load_async(g0 + 16 * (c + 1), vn);
+        epi_math16(e, n0 + g0 + 16 * c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ss += v[j] * v[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = vn[j];
+      }
+      inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    load_async(g0, v);
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      wait(v);
+      if (c + 1 < NCH) load_async(g0 + 16 * (c + 1), vn);
+      epi_math16(e, n0 + g0 + 16 * c, v);
+      if (l2) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + 16 * c + j));
+          v[j] *= inv * s4.x; v[j + 1] *= inv * s4.y; v[j + 2] *= inv * s4.z; v[j + 3] *= inv * s4.w;
+        }
+      }
+      epi_store16<SIMPLE>(p, ri, n0 + g0 + 16 * c, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = vn[j];
     }
   }
 }
 
-// tcgen05.ld of N32*32 columns into v, completion deferred to tmem_wait_regs
-template <int N32>
-__device__ __forceinline__ void tmem_ld_async(uint32_t taddr, float* v) {
-#pragma unroll
-  for (int i = 0; i < N32; ++i) tmem_ld32_nowait(taddr + 32 * i, reinterpret_cast<uint32_t*>(v) + 32 * i);
-}
-// wait::ld, then pin every destination register behind the wait so the compiler cannot hoist their uses above it
-template <int N>
-__device__ __forceinline__ void tmem_wait_regs(float* v) {
+// wait::ld, then pin the 16 destination registers behind the wait so the compiler cannot hoist their uses above it
+__device__ __forceinline__ void tmem_wait_regs16(float* v) {
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
+  for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(v[i]));
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 kernel
@@ -250,7 +269,7 @@ __device__ __forceinline__ void tmem_wait_regs(float* v) {
 // tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SIMPLE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -366,9 +385,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-      constexpr int EG = BN >= 64 ? 64 : BN;
-      epilogue_row<BN>(p, ri, n0, [&](int c, float* v) { tmem_ld_async<EG / 32>(taddr + (uint32_t)c, v); },
-                       [&](float* v) { tmem_wait_regs<EG>(v); });
+      epilogue_row<BN, SIMPLE>(p, ri, n0, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                       [&](float* v) { tmem_wait_regs16(v); });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -433,10 +451,9 @@ __global__ void conv_gemm_ref_epilogue_kernel(GemmParams p, const float* __restr
   if (p.epi.rows_per_group > 0)
     ri.orow = (m / p.epi.rows_per_group) * (long long)p.epi.group_stride + p.epi.row_offset + (m % p.epi.rows_per_group);
   const float* src = scratch + m * p.Npad + ch * BNW;
-  constexpr int EG = BNW >= 64 ? 64 : BNW;
-  epilogue_row<BNW>(p, ri, ch * BNW, [&](int c, float* v) {
+  epilogue_row<BNW, false>(p, ri, ch * BNW, [&](int c, float* v) {
 #pragma unroll
-    for (int j = 0; j < EG; ++j) v[j] = src[c + j];
+    for (int j = 0; j < 16; ++j) v[j] = src[c + j];
   }, [](float*) {});
 }
 
@@ -448,19 +465,28 @@ int next_pow2(int v) {
   return r;
 }
 
-template <int BN, int STAGES>
-int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams& p, int ntiles, cudaStream_t st) {
+template <int BN, int STAGES, bool SIMPLE>
+int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams& p, int ntiles, cudaStream_t st) {
   constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const long long total = (long long)ntiles * (p.Npad / BN);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, GEMM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
   B200_LAUNCH_OK();
   return B200_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams& p, int ntiles, cudaStream_t st) {
+  const EpiDev& e = p.epi;
+  const bool simple = e.out_mode == B200_OUT_BF16 && e.split_col == 0 && e.rows_per_group == 0 && e.dup_rows == 0 && e.l2_cols == 0 &&
+                      (p.N & 15) == 0 && (e.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
+                      (e.residual == nullptr || ((e.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0));
+  return simple ? launch_tc2<BN, STAGES, true>(maps, mapB, p, ntiles, st) : launch_tc2<BN, STAGES, false>(maps, mapB, p, ntiles, st);
 }
 
 }  // namespace

@@ -35,8 +35,8 @@ def log_snr_to_alpha_sigma(log_snr):                  # imagen_pytorch.py:220-22
 LOG_SNR = {'linear': beta_linear_log_snr, 'cosine': alpha_cosine_log_snr}
 
 
-def sampling_timesteps(num_timesteps, batch):         # get_sampling_timesteps, imagen_pytorch.py:245-250
-    times = torch.linspace(1., 0., num_timesteps + 1)
+def sampling_timesteps(num_timesteps, batch, device='cpu'):         # get_sampling_timesteps, imagen_pytorch.py:245-250
+    times = torch.linspace(1., 0., num_timesteps + 1, device=device)
     times = times[None, :].expand(batch, -1)
     times = torch.stack((times[:, :-1], times[:, 1:]), dim=0)
     return times.unbind(dim=-1)
@@ -80,7 +80,7 @@ def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, con
     log_snr_fn = LOG_SNR[schedule]
     batch = shape[0]
     img = randn(shape)                                                         # :2195
-    for times, times_next in sampling_timesteps(timesteps, batch):             # :2242
+    for times, times_next in sampling_timesteps(timesteps, batch, img.device):  # :2242
         pred = unet_fn(img, log_snr_fn(times), cond_scale=cond_scale,
                        lowres_noise_times=lowres_log_snr, **unet_kwargs)       # :2072-2083
         pad = lambda v: v.view(-1, 1, 1, 1)

@@ -116,7 +116,7 @@ def _perceiver_resampler(x, sd, p, heads):            # imagen_pytorch.py:481-49
     latents = sd[p + '.latents'].unsqueeze(0).expand(x.shape[0], -1, -1)
     mp = p + '.to_latents_from_mean_pooled_seq'
     if (mp + '.1.weight') in sd:
-        pooled = x.sum(dim=1) / torch.full((x.shape[0], 1), float(n)).clamp(min=1e-5)   # masked_mean with all-ones mask :490,:142-150
+        pooled = x.sum(dim=1) / torch.full((x.shape[0], 1), float(n), device=x.device).clamp(min=1e-5)   # masked_mean with all-ones mask :490,:142-150
         ml = _ln_gain(pooled, sd[mp + '.0.g'])
         ml = _linear(ml, sd, mp + '.1')
         ml = ml.view(x.shape[0], -1, x.shape[-1])
@@ -283,7 +283,7 @@ def unet_forward(sd, cfg, x, time, *, text_embeds=None, text_mask=None,
     # text conditioning :1595-1652
     text_tokens = None
     if text_embeds is not None and cfg['cond_on_text']:
-        keep = torch.full((batch,), cond_drop_prob != 1., dtype=torch.bool)    # prob_mask_like :201-207 (prob in {0,1})
+        keep = torch.full((batch,), cond_drop_prob != 1., dtype=torch.bool, device=x.device)    # prob_mask_like :201-207 (prob in {0,1})
         assert cond_drop_prob in (0., 1.), 'oracle covers the sampling path only (no random dropout)'
         max_len = cfg['max_text_len']
         text_tokens = _linear(text_embeds, sd, 'text_to_cond')[:, :max_len]
