@@ -20,6 +20,7 @@
 // Replaces the same reference arithmetic as attention.cu (Attention.forward / CrossAttention.forward einsum ->
 // softmax -> einsum, imagen_pytorch.py:565-588, :818-833).
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -27,8 +28,8 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_SM_WARPS = 16;                    // softmax warps: 4 per scheduler sub-partition
-constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;  // + TMA warp + MMA warp
+constexpr int FA_MAX_SM_WARPS = 16;
+constexpr int FA_DEFAULT_VARIANT = 9;
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
@@ -50,7 +51,8 @@ struct FaParams {
   float max_logit;
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+template <int NW, bool PF, bool WA>
+__global__ void __launch_bounds__(64 + 32 * NW, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t fa_smem_raw[];
@@ -83,8 +85,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 32 * FA_SM_WARPS);   // every softmax thread arrives after its tcgen05.ld of the buffer
-      mbar_init(&p_full[s], 32 * FA_SM_WARPS);    // every softmax thread arrives after writing its slice of the P row
+      mbar_init(&s_empty[s], WA ? NW : 32 * NW);   // softmax threads (or one lane per warp) arrive after their tcgen05.ld of the buffer
+      mbar_init(&p_full[s], WA ? NW : 32 * NW);    // ... and after writing their slice of the P row
       mbar_init(&p_empty[s], 1);
     }
     mbar_init(o_full, 1);
@@ -160,42 +162,65 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       umma_commit(o_full);
     }
   } else {
-    // ---------------- softmax / epilogue warps 2..17: thread = (query row, 32-key slice of every key tile).
-    // Four warps per scheduler sub-partition, and the TMEM read of tile j+1 is in flight while tile j is exponentiated,
-    // so the MUFU pipe (the real bound of head-dim-64 attention: 4*64 MMA flops per exp) stays busy.
+    // ---------------- softmax / epilogue warps: thread = (query row, CPT-key slice of every key tile), NW/4 warps per
+    // scheduler sub-partition.  With PF the TMEM read of tile j+1 is in flight while tile j is exponentiated.
+    constexpr int NSL = NW / 4;             // column slices
+    constexpr int CPT = FA_BN / NSL;        // key columns per thread per tile: 128 / 64 / 32
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int slice = (warp - 2) >> 2;      // keys [32*slice, 32*slice + 32) of every tile
+    const int slice = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float l = 0.f;
     const float C = p.max_logit;
-    uint32_t cur[32], nxt[32];
-    mbar_wait(&s_full[0], 0);
-    tc_fence_after();
-    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(slice * 32), cur);
-    tmem_ld_wait();
+    uint32_t cur[CPT];
+    uint32_t nxt[PF ? CPT : 1];
+    auto arrive = [&](uint64_t* bar) {
+      if (WA) { __syncwarp(); if (lane == 0) mbar_arrive(bar); }
+      else mbar_arrive(bar);
+    };
+    auto load_s = [&](int buf, uint32_t* dst) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(cur[i]));   // pin the destination registers behind the wait
-    tc_fence_before();
-    mbar_arrive(&s_empty[0]);
+      for (int c = 0; c < CPT; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(buf * FA_BN + slice * CPT + c), dst + c);
+    };
+    if (PF) {
+      mbar_wait(&s_full[0], 0);
+      tc_fence_after();
+      load_s(0, cur);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(cur[i]));   // pin the destination registers behind the wait
+      tc_fence_before();
+      arrive(&s_empty[0]);
+    }
     for (int j = 0; j < ntiles; ++j) {
       const int buf = j & 1;
       const uint32_t par = (uint32_t)((j >> 1) & 1);
       const bool more = j + 1 < ntiles;
-      if (more) {                               // start reading S_{j+1} (issued by the MMA warp one tile ahead)
-        const int nb = (j + 1) & 1;
-        mbar_wait(&s_full[nb], (uint32_t)(((j + 1) >> 1) & 1));
+      if (PF) {
+        if (more) {                             // start reading S_{j+1} (issued by the MMA warp one tile ahead)
+          const int nb = (j + 1) & 1;
+          mbar_wait(&s_full[nb], (uint32_t)(((j + 1) >> 1) & 1));
+          tc_fence_after();
+          load_s(nb, nxt);
+        }
+        mbar_wait(&p_empty[buf], par ^ 1u);     // the P V MMA that read P[buf] two tiles ago has finished
+      } else {
+        mbar_wait(&s_full[buf], par);
         tc_fence_after();
-        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(nb * FA_BN + slice * 32), nxt);
-      }
-      mbar_wait(&p_empty[buf], par ^ 1u);       // the P V MMA that read P[buf] two tiles ago has finished
-      const int key0 = j * FA_BN + slice * 32;
-      const bool ragged = key0 + 32 > p.n_keys;
-      // this thread's 64 bytes of the P row: chunks 4*(slice&1) .. +3 of the 64-key block slice>>1
-      uint8_t* prow = sP + buf * FA_P_BYTES + (slice >> 1) * (FA_BM * 128) + r * 128;
-      const int ch0 = (slice & 1) * 4;
+        load_s(buf, cur);
+        mbar_wait(&p_empty[buf], par ^ 1u);
+        tmem_ld_wait();
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+        for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(cur[i]));
+        tc_fence_before();
+        arrive(&s_empty[buf]);                  // S[buf] is in registers: the tensor pipe may overwrite it with tile j+2
+      }
+      const int key0 = j * FA_BN + slice * CPT;
+      const bool ragged = key0 + CPT > p.n_keys;
+      // this thread's CPT*2 bytes of the P row: 16-byte chunks of the 64-key blocks, XOR-swizzled by the row
+      uint8_t* prow = sP + buf * FA_P_BYTES + r * 128;
+#pragma unroll
+      for (int t = 0; t < CPT / 8; ++t) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
@@ -208,37 +233,250 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           l += p0 + p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        // 16-byte chunk of the row, XOR-swizzled by the row (the layout TMA / UMMA use for SWIZZLE_128B)
-        *reinterpret_cast<uint4*>(prow + (((ch0 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        const int col = slice * CPT + 8 * t;    // first key column of this 16-byte chunk within the tile
+        *reinterpret_cast<uint4*>(prow + (col >> 6) * (FA_BM * 128) + ((((col & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();                 // make the generic-proxy P writes visible to the tensor-core (async) proxy
-      mbar_arrive(&p_full[buf]);
-      if (more) {
+      arrive(&p_full[buf]);
+      if (PF && more) {
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(nxt[i]));
+        for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(nxt[i]));
         tc_fence_before();
-        mbar_arrive(&s_empty[(j + 1) & 1]);     // S_{j+1} is in registers: the tensor pipe may overwrite the buffer with tile j+3
+        arrive(&s_empty[(j + 1) & 1]);          // S_{j+1} is in registers: the tensor pipe may overwrite the buffer with tile j+3
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+        for (int i = 0; i < CPT; ++i) cur[i] = nxt[i];
       }
     }
-    // ---- O / l -> global: each slice stores 16 of the 64 output channels
+    // ---- O / l -> global: each slice stores 64/NSL of the 64 output channels
     sL[slice * FA_BM + r] = l;
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * FA_SM_WARPS) : "memory");   // softmax warps only
-    const float inv = 1.f / (sL[r] + sL[FA_BM + r] + sL[2 * FA_BM + r] + sL[3 * FA_BM + r]);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");   // softmax warps only
+    float lsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NSL; ++i) lsum += sL[i * FA_BM + r];
+    const float inv = 1.f / lsum;
     mbar_wait(o_full, 0);
     tc_fence_after();
+    constexpr int OC = FA_D / NSL;          // 64 / 32 / 16 output channels per thread
     const int row = row0 + r;
-    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + slice * 16;
-    uint32_t orr[16];
-    tmem_ld16_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * 16), orr);
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + slice * OC;
+    uint32_t orr[OC];
+    if (OC == 16) tmem_ld16_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * OC), orr);
+    else {
+#pragma unroll
+      for (int c = 0; c < OC; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * OC + c), orr + c);
+    }
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(orr[i]));
+    for (int i = 0; i < OC; ++i) asm volatile("" : "+r"(orr[i]));
     if (row < p.rows) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < OC / 8; ++t) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + 8 * t) = u;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ping-pong variant: TWO 128-row query tiles (groups A and B) per CTA share one K/V stream.  Each group has its own
+// S accumulator, P buffer, O accumulator and four softmax warps; while one group waits on its TMEM read / proxy fence /
+// barrier round trip the other one exponentiates, and the S of the next key tile is issued as soon as a group has
+// pulled its current scores into registers.  (Measured on B200: in the one-tile kernel above the softmax warps issue only
+// ~27% of the time regardless of their number -- the per-tile dependency chain, not MUFU, was the limit.)
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PP_THREADS = 64 + 256;
+constexpr int PP_SMEM = 2 * FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [2] query tiles
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [STAGES] {K, V}
+  uint8_t* sP = sKV + FA_STAGES * FA_KV_BYTES;          // [2] one P buffer per group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+  uint64_t* q_full = bars;                       // [1]
+  uint64_t* kv_full = bars + 1;                  // [STAGES]
+  uint64_t* kv_empty = kv_full + FA_STAGES;      // [STAGES]
+  uint64_t* s_full = kv_empty + FA_STAGES;       // [2] per group
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* p_full = s_empty + 2;                // [2]
+  uint64_t* p_empty = p_full + 2;                // [2]
+  uint64_t* o_full = p_empty + 2;                // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * (2 * FA_BM);
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 128);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&p_empty[g], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: both query tiles, then the K/V ring
+      mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
+      for (int g = 0; g < 2; ++g) {
+        if (p.q_heads_first) tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, h, row0 + g * FA_BM, b);
+        else tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, row0 + g * FA_BM, h, b);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % FA_STAGES;
+        const uint32_t n = (uint32_t)(j / FA_STAGES);
+        mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
+        uint8_t* dst = sKV + st * FA_KV_BYTES;
+        if (p.kv_heads_first) {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+        } else {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer for both groups
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      auto issue_s = [&](int j, int g) {        // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
+        const int st = j % FA_STAGES;
+        mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(g * FA_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) {
+          mbar_wait(&kv_full[(j + 1) % FA_STAGES], (uint32_t)(((j + 1) / FA_STAGES) & 1));
+          issue_s(j + 1, 0);
+          issue_s(j + 1, 1);
+        }
+        const int st = j % FA_STAGES;
+        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], (uint32_t)(j & 1));   // group g wrote P_g(j)
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(sP + g * FA_P_BYTES);
+#pragma unroll
+          for (int k = 0; k < FA_BN / 16; ++k) {
+            const uint64_t adesc = make_sw128_kmajor_desc(p_addr + (uint32_t)((k >> 2) * (FA_BM * 128) + (k & 3) * 32));
+            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)(k * 16 * 128), 1024, 1024);
+            umma_bf16(tmem_base + (uint32_t)(256 + g * FA_D), adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&p_empty[g]);
+        }
+        umma_commit(&kv_empty[st]);           // K_j / V_j consumed by both groups
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ---------------- softmax / epilogue: group g = (warp - 2) / 4, thread = query row of that group
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float l = 0.f;
+    const float C = p.max_logit;
+    uint8_t* prow = sP + g * FA_P_BYTES + r * 128;
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      const int key0 = j * FA_BN;
+      const bool ragged = key0 + FA_BN > p.n_keys;
+      // two halves of 64 score columns: 64 live registers instead of 128
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sr[64];
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64), sr);
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + 32), sr + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
+        if (hf == 1) {
+          tc_fence_before();
+          mbar_arrive(&s_empty[g]);             // all of S_g is in registers: the tensor pipe may start S_g(j+1)
+        } else {
+          mbar_wait(&p_empty[g], par ^ 1u);     // the P V MMA of the previous key tile has finished reading P_g
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
+            float p1 = ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
+            if (ragged) {
+              if (key0 + hf * 64 + 8 * t + i >= p.n_keys) p0 = 0.f;
+              if (key0 + hf * 64 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
+            }
+            l += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + hf * (FA_BM * 128) + ((t ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g]);
+    }
+    // ---- O / l -> global
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = row0 + g * FA_BM + r;
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs;
+    uint32_t orr[FA_D];
+    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + g * FA_D), orr);
+    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + g * FA_D + 32), orr + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < FA_D; ++i) asm volatile("" : "+r"(orr[i]));
+    if (row < p.rows) {
+#pragma unroll
+      for (int t = 0; t < FA_D / 8; ++t) {
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
         u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
@@ -299,13 +537,44 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.q_bs = q_bs; p.q_hs = q_hs; p.q_rs = q_rs; p.rows = rows; p.n_keys = n_keys; p.max_logit = max_logit;
   p.q_heads_first = q_hf ? 1 : 0; p.kv_heads_first = kv_hf ? 1 : 0;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    configured = true;
-  }
   dim3 grid((rows + FA_BM - 1) / FA_BM, n_heads, B);
-  flash_attn_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mk, mv, p);
+  // kernel variant: (softmax warps, S prefetch, warp-level barrier arrive).  Default chosen from B200 measurements
+  // (profiles/); B200_IMAGEN_FA_VARIANT overrides it for the tuning sweep in tools/sweep_attention.py.
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("B200_IMAGEN_FA_VARIANT");
+    variant = e ? atoi(e) : FA_DEFAULT_VARIANT;
+  }
+#define FA_LAUNCH(NW, PF, WA)                                                                                                      \
+  {                                                                                                                                \
+    static bool configured = false;                                                                                                \
+    if (!configured) {                                                                                                             \
+      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_tc_kernel<NW, PF, WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));  \
+      configured = true;                                                                                                           \
+    }                                                                                                                              \
+    flash_attn_tc_kernel<NW, PF, WA><<<grid, 64 + 32 * NW, FA_SMEM, st>>>(mq, mk, mv, p);                                         \
+  }
+  switch (variant) {
+    case 0: FA_LAUNCH(4, false, false); break;
+    case 1: FA_LAUNCH(8, false, false); break;
+    case 2: FA_LAUNCH(8, true, false); break;
+    case 3: FA_LAUNCH(16, false, false); break;
+    case 4: FA_LAUNCH(16, true, false); break;
+    case 5: FA_LAUNCH(8, false, true); break;
+    case 6: FA_LAUNCH(8, true, true); break;
+    case 7: FA_LAUNCH(16, true, true); break;
+    case 8: FA_LAUNCH(4, false, true); break;
+    default: {   // ping-pong: two query tiles per CTA
+      static bool configured = false;
+      if (!configured) {
+        B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
+        configured = true;
+      }
+      dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);
+      flash_attn_pp_kernel<<<grid2, PP_THREADS, PP_SMEM, st>>>(mq, mk, mv, p);
+    } break;
+  }
+#undef FA_LAUNCH
   B200_LAUNCH_OK();
   return B200_OK;
 }
