@@ -291,14 +291,19 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // Ping-pong variant: TWO 128-row query tiles (groups A and B) per CTA share one K/V stream.  Each group has its own
-// S accumulator, P buffer, O accumulator and four softmax warps; while one group waits on its TMEM read / proxy fence /
-// barrier round trip the other one exponentiates, and the S of the next key tile is issued as soon as a group has
-// pulled its current scores into registers.  (Measured on B200: in the one-tile kernel above the softmax warps issue only
-// ~27% of the time regardless of their number -- the per-tile dependency chain, not MUFU, was the limit.)
+// MMA issuer thread, S accumulator, double-buffered P, O accumulator and four softmax warps, so the groups are fully
+// decoupled: while one waits on its TMEM read / proxy fence / barrier round trip the other one exponentiates, and the S
+// of the next key tile is issued as soon as a group has pulled its current scores into registers.
+// (Measured on B200: in the one-tile kernel above the softmax warps issue only ~27% of the time regardless of their
+// number -- the per-tile dependency chain, not MUFU, was the limit; a first ping-pong with ONE issuer thread and a
+// single P buffer per group still had the softmax warps waiting on p_empty / the in-order issuer: 1.91 ms.)
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// warps: 0 TMA, 1 issuer A (+TMEM alloc), 2 issuer B, 3 idle, 4-7 softmax A, 8-11 softmax B.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PP_THREADS = 64 + 256;
-constexpr int PP_SMEM = 2 * FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256;
+constexpr int PP_THREADS = 384;
+constexpr int PP_STAGES = 4;                       // deep K/V ring: the two groups may drift apart by more than a tile
+constexpr int PP_PH_BYTES = FA_BM * 64 * 2;        // one 64-key half of a P tile (16 KB), its own full/empty barriers
+constexpr int PP_SMEM = 2 * FA_Q_BYTES + PP_STAGES * FA_KV_BYTES + 4 * PP_PH_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
 flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -306,18 +311,18 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // [2] query tiles
-  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [STAGES] {K, V}
-  uint8_t* sP = sKV + FA_STAGES * FA_KV_BYTES;          // [2] one P buffer per group
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [PP_STAGES] {K, V}
+  uint8_t* sP = sKV + PP_STAGES * FA_KV_BYTES;          // [group][half] 64-key halves of the P tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * PP_PH_BYTES);
   uint64_t* q_full = bars;                       // [1]
-  uint64_t* kv_full = bars + 1;                  // [STAGES]
-  uint64_t* kv_empty = kv_full + FA_STAGES;      // [STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;       // [2] per group
-  uint64_t* s_empty = s_full + 2;                // [2]
-  uint64_t* p_full = s_empty + 2;                // [2]
-  uint64_t* p_empty = p_full + 2;                // [2]
-  uint64_t* o_full = p_empty + 2;                // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* kv_full = bars + 1;                  // [4]
+  uint64_t* kv_empty = bars + 5;                 // [4]   (count 2: both groups' P V MMAs)
+  uint64_t* s_full = bars + 9;                   // [group]
+  uint64_t* s_empty = bars + 11;                 // [group]
+  uint64_t* p_full = bars + 13;                  // [group][half]
+  uint64_t* p_empty = bars + 17;                 // [group][half]
+  uint64_t* o_full = bars + 21;                  // [group]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * (2 * FA_BM);
@@ -329,14 +334,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < PP_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&s_empty[g], 128);
-      mbar_init(&p_full[g], 128);
-      mbar_init(&p_empty[g], 1);
+      mbar_init(&o_full[g], 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }   // per 64-key half
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
@@ -354,8 +358,8 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         else tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, row0 + g * FA_BM, h, b);
       }
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % FA_STAGES;
-        const uint32_t n = (uint32_t)(j / FA_STAGES);
+        const int st = j % PP_STAGES;
+        const uint32_t n = (uint32_t)(j / PP_STAGES);
         mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
         mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
         uint8_t* dst = sKV + st * FA_KV_BYTES;
@@ -368,62 +372,57 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
     if (lane == 0) {
-      // ---------------- MMA issuer for both groups
+      // ---------------- MMA issuer of group g
+      const int g = warp - 1;
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      auto issue_s = [&](int j, int g) {        // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
-        const int st = j % FA_STAGES;
+      const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+      auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
+        const int st = j % PP_STAGES;
+        mbar_wait(&kv_full[st], (uint32_t)((j / PP_STAGES) & 1));
         mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
         tc_fence_after();
-        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(g * FA_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[g]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      issue_s(0, 0);
-      issue_s(0, 1);
+      issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) {
-          mbar_wait(&kv_full[(j + 1) % FA_STAGES], (uint32_t)(((j + 1) / FA_STAGES) & 1));
-          issue_s(j + 1, 0);
-          issue_s(j + 1, 1);
-        }
-        const int st = j % FA_STAGES;
+        if (j + 1 < ntiles) issue_s(j + 1);
+        const int st = j % PP_STAGES;
         const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], (uint32_t)(j & 1));   // group g wrote P_g(j)
+        for (int hf = 0; hf < 2; ++hf) {        // the first 64 keys are multiplied while the second 64 are exponentiated
+          const int pb = 2 * g + hf;
+          mbar_wait(&p_full[pb], (uint32_t)(j & 1));
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(sP + g * FA_P_BYTES);
+          const uint32_t p_addr = smem_u32(sP + pb * PP_PH_BYTES);
 #pragma unroll
-          for (int k = 0; k < FA_BN / 16; ++k) {
-            const uint64_t adesc = make_sw128_kmajor_desc(p_addr + (uint32_t)((k >> 2) * (FA_BM * 128) + (k & 3) * 32));
-            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)(k * 16 * 128), 1024, 1024);
-            umma_bf16(tmem_base + (uint32_t)(256 + g * FA_D), adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_sw128_kmajor_desc(p_addr + (uint32_t)(k * 32));
+            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((hf * 4 + k) * 16 * 128), 1024, 1024);
+            umma_bf16(tmem_base + (uint32_t)(256 + g * FA_D), adesc, bdesc, idesc_pv, (j | hf | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&p_empty[g]);
+          umma_commit(&p_empty[pb]);
         }
-        umma_commit(&kv_empty[st]);           // K_j / V_j consumed by both groups
+        umma_commit(&kv_empty[st]);             // one of the two arrivals that free K_j / V_j
       }
-      umma_commit(o_full);
+      umma_commit(&o_full[g]);
     }
-  } else {
-    // ---------------- softmax / epilogue: group g = (warp - 2) / 4, thread = query row of that group
-    const int g = (warp - 2) >> 2;
+  } else if (warp >= 4) {
+    // ---------------- softmax / epilogue: group g, thread = query row of that group
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float l = 0.f;
     const float C = p.max_logit;
-    uint8_t* prow = sP + g * FA_P_BYTES + r * 128;
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t par = (uint32_t)(j & 1);
-      mbar_wait(&s_full[g], par);
+      mbar_wait(&s_full[g], (uint32_t)(j & 1));
       tc_fence_after();
       const int key0 = j * FA_BN;
       const bool ragged = key0 + FA_BN > p.n_keys;
@@ -438,10 +437,11 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
         if (hf == 1) {
           tc_fence_before();
-          mbar_arrive(&s_empty[g]);             // all of S_g is in registers: the tensor pipe may start S_g(j+1)
-        } else {
-          mbar_wait(&p_empty[g], par ^ 1u);     // the P V MMA of the previous key tile has finished reading P_g
+          mbar_arrive(&s_empty[g]);             // all of S_g is in registers: issuer g may start S_g(j+1)
         }
+        const int pb = 2 * g + hf;
+        uint8_t* prow = sP + pb * PP_PH_BYTES + r * 128;
+        mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           uint32_t pk[4];
@@ -456,14 +456,14 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             l += p0 + p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          *reinterpret_cast<uint4*>(prow + hf * (FA_BM * 128) + ((t ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + ((t ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[pb]);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[g]);
     }
     // ---- O / l -> global
-    mbar_wait(o_full, 0);
+    mbar_wait(&o_full[g], 0);
     tc_fence_after();
     const float inv = 1.f / l;
     const int row = row0 + g * FA_BM + r;

@@ -200,3 +200,56 @@ def test_full_size_sampling_smoke_dim128():
     out = im.sample(text_embeds=torch.randn(4, 256, 768, device=DEV), cond_scale=3., use_tqdm=False)
     assert out.shape == (4, 3, 64, 64) and out.min() >= 0 and out.max() <= 1 and torch.isfinite(out).all()
     assert out.std() > 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ the other BASELINE.json configurations (smoke + properties)
+
+def _rand_final_conv(u):
+    with torch.no_grad():
+        u.final_conv.weight.normal_(0, 0.02)
+        u.final_conv.bias.normal_(0, 0.02)
+    return u
+
+
+def test_cfg3_elucidated_dim128_smoke():
+    """BASELINE.json configs[2] architecture: ElucidatedImagen(Unet(dim=128)) @64x64 (fewer steps / smaller batch)."""
+    torch.manual_seed(0)
+    el = b2.ElucidatedImagen(_rand_final_conv(b2.Unet(dim=128)), image_sizes=64, num_sample_steps=6).to(DEV)
+    te = torch.randn(4, 256, 768, device=DEV)
+    torch.manual_seed(1)
+    a = el.sample(text_embeds=te, cond_scale=3., use_tqdm=False)
+    torch.manual_seed(1)
+    b = el.sample(text_embeds=te, cond_scale=3., use_tqdm=False)
+    assert a.shape == (4, 3, 64, 64) and torch.equal(a, b) and torch.isfinite(a).all() and 0 <= a.min() and a.max() <= 1
+    assert el.last_launch_count > 0
+
+
+def test_cfg4_cascade_64_to_256_srunet256_smoke():
+    """BASELINE.json configs[3] architecture: base Unet(dim=128) @64 -> SRUnet256 (memory_efficient, lowres_cond) @256."""
+    torch.manual_seed(0)
+    base, sr = _rand_final_conv(b2.Unet(dim=128)), _rand_final_conv(b2.SRUnet256(lowres_cond=True))
+    im = b2.Imagen((base, sr), image_sizes=(64, 256), timesteps=3).to(DEV)
+    te = torch.randn(2, 256, 768, device=DEV)
+    torch.manual_seed(2)
+    outs = im.sample(text_embeds=te, cond_scale=3., use_tqdm=False, return_all_unet_outputs=True)
+    assert outs[0].shape == (2, 3, 64, 64) and outs[1].shape == (2, 3, 256, 256)
+    assert all(torch.isfinite(o).all() and 0 <= o.min() and o.max() <= 1 for o in outs)
+    # upscale-only entry point (start_at_unet_number, imagen_pytorch.py:2396-2403) reproduces stage 2 given the same noise
+    torch.manual_seed(3)
+    a = im.sample(text_embeds=te, cond_scale=3., use_tqdm=False, start_at_unet_number=2, start_image_or_video=outs[0])
+    torch.manual_seed(3)
+    b = im.sample(text_embeds=te, cond_scale=3., use_tqdm=False, start_at_unet_number=2, start_image_or_video=outs[0])
+    assert torch.equal(a, b) and a.shape == (2, 3, 256, 256)
+
+
+def test_cfg5_dim192_forward_properties():
+    """BASELINE.json configs[4] architecture: base Unet(dim=192) (channels up to 2304 in the concat norms)."""
+    torch.manual_seed(0)
+    u = _rand_final_conv(b2.Unet(dim=192)).to(DEV)
+    x, t = torch.randn(2, 3, 64, 64, device=DEV), torch.tensor([1.0, -1.0], device=DEV)
+    te = torch.randn(2, 256, 768, device=DEV)
+    a, b = u(x, t, text_embeds=te), u(x, t, text_embeds=te)
+    assert torch.equal(a, b) and torch.isfinite(a).all() and a.abs().max() > 1e-3
+    # per-sample independence: sample 0 alone gives the same result as inside the batch (no cross-sample ops on the path)
+    a0 = u(x[:1], t[:1], text_embeds=te[:1])
+    assert torch.allclose(a0, a[:1], rtol=0, atol=1e-5)
