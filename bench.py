@@ -118,6 +118,31 @@ def time_attention_kernel(bs_rows, device, iters=10, max_logit=8 * 1.44269504088
     return e0.elapsed_time(e1) / iters
 
 
+def time_conv_kernel(R, device, iters=20):
+    """The heaviest conv shape of the workload alone: 64x64 level Block.project, 3x3, 128 -> 128 channels, R rows (NHWC bf16)."""
+    from imagen_pytorch_b200 import ops, _lib
+    x = torch.randn(R, 64, 64, 128, device=device).to(torch.bfloat16)
+    Wt = torch.randn(128, 128, 3, 3, device=device) / 34.0
+    segs, mats = ops.conv_segments(Wt, [128])
+    wp = ops.pack_weight(mats, 128, device)
+    out = torch.empty(R * 4096, 128, dtype=torch.bfloat16, device=device)
+    call = ops.GemmCall([(x.data_ptr(), 128, 128)], segs, (R, 64, 64), wp, 128, out.data_ptr(), bias=ops.padded_bias(torch.zeros(128, device=device), 128, device), ldc=128)
+    st = torch.cuda.current_stream(device)
+    for _ in range(3):
+        call(st.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > 126 MB L2: flushed between launches
+    times = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        call(st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize(device)
+        times.append(e0.elapsed_time(e1))
+    return statistics.median(times), 2.0 * R * 4096 * 128 * 1152 / 1e9
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on an
     8-CPU quota thrashes: round 1 measured 50 s per step that way)."""
@@ -286,10 +311,20 @@ def main():
         R = 2 * args.bs
         att_ms = time_attention_kernel(R, device)
         att_tflops = ATTN_L0_GFLOP_PER_SAMPLE * R / 1e3 / (att_ms / 1e3)
-        line['roofline'] = {'kernel': 'flash_attn_tc_kernel (tcgen05 multi-query self-attention, 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
+        # MUFU floor of head-dim-64 attention: one exp2 per score, 16 exp2/clk/SM measured (profiles/r01_mufu_ex2_microbench.txt)
+        n_exp = R * 8 * 4096 * ((4096 + 39 + 127) // 128 * 128)
+        mufu_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
+        line['roofline'] = {'kernel': 'flash_attn_pp_kernel (tcgen05 multi-query self-attention, 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
                             'bound': 'tensor', 'achieved': att_tflops, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': att_tflops / pk['tensor_burst'],
-                            'traffic': None, 'ms_per_launch': att_ms, 'algorithmic_gflop_per_launch': ATTN_L0_GFLOP_PER_SAMPLE * R,
-                            'peak_source': f"{pk['src']} burst bf16 (kernel timed alone)"}
+                            'traffic': 262.4e6, 'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_flash_attn_pp_summary.txt); algorithmic q+o+k+v = 285 MB',
+                            'ms_per_launch': att_ms, 'algorithmic_gflop_per_launch': ATTN_L0_GFLOP_PER_SAMPLE * R,
+                            'peak_source': f"{pk['src']} burst bf16 (kernel timed alone)",
+                            'mufu_floor_ms': mufu_ms, 'frac_of_mufu_floor': mufu_ms / att_ms}
+        conv_ms, conv_gflop = time_conv_kernel(R, device)
+        line['roofline_conv'] = {'kernel': 'conv_gemm_tc_kernel<128,6,SIMPLE> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64)', 'bound': 'tensor',
+                                 'achieved': conv_gflop / conv_ms, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': conv_gflop / conv_ms / pk['tensor_burst'],
+                                 'traffic': 34.0e6, 'ms_per_launch': conv_ms, 'algorithmic_gflop_per_launch': conv_gflop,
+                                 'note': 'L2 flushed between launches; dram traffic from ncu = 33.9 MB read (input 33.5 MB read once), output stays in L2'}
         step_tflop = GFLOP_PER_FORWARD_DIM128 * 2 * args.bs * args.timesteps / 1e3 if args.dim == 128 else None
         if step_tflop:
             ach = step_tflop / (ms / args.steps / 1e3)
