@@ -29,7 +29,7 @@ constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
 constexpr int FA_MAX_SM_WARPS = 16;
-constexpr int FA_DEFAULT_VARIANT = 9;
+constexpr int FA_DEFAULT_VARIANT = 10;   // ping-pong, 1/4 of the exponentials on the FMA pipe (profiles/r01_attention_variant_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
@@ -41,6 +41,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// exp2 on the FMA/ALU pipes (Cody-Waite split + cubic): the MUFU pipe delivers only 16 exp2/clk/SM, which is THE bound of
+// head-dim-64 attention; moving a fraction of the exponentials here frees MUFU issue slots.  |rel err| < 7e-4 (P is bf16).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float magic = 12582912.f;                 // 1.5 * 2^23: the add rounds x to the nearest integer in the low mantissa bits
+  const float xm = x + magic;
+  const float f = x - (xm - magic);               // fractional part in [-0.5, 0.5]
+  float p = fmaf(f, 0.05550410866f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xm) << 23));   // * 2^n through the exponent field
 }
 
 struct FaParams {
@@ -305,6 +318,7 @@ constexpr int PP_STAGES = 4;                       // deep K/V ring: the two gro
 constexpr int PP_PH_BYTES = FA_BM * 64 * 2;        // one 64-key half of a P tile (16 KB), its own full/empty barriers
 constexpr int PP_SMEM = 2 * FA_Q_BYTES + PP_STAGES * FA_KV_BYTES + 4 * PP_PH_BYTES + 1024 + 256;
 
+template <int POLY>   // every POLY-th exponential goes to the FMA pipe (0 = all on MUFU)
 __global__ void __launch_bounds__(PP_THREADS, 1)
 flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
@@ -448,7 +462,8 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
             float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
-            float p1 = ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
+            float p1 = (POLY > 0 && ((8 * t + i + 1) % POLY) == POLY - 1) ? ex2_poly(__uint_as_float(sr[8 * t + i + 1]) - C)
+                                                                         : ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
             if (ragged) {
               if (key0 + hf * 64 + 8 * t + i >= p.n_keys) p0 = 0.f;
               if (key0 + hf * 64 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
@@ -564,15 +579,20 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 6: FA_LAUNCH(8, true, true); break;
     case 7: FA_LAUNCH(16, true, true); break;
     case 8: FA_LAUNCH(4, false, true); break;
-    default: {   // ping-pong: two query tiles per CTA
-      static bool configured = false;
-      if (!configured) {
-        B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
-        configured = true;
-      }
-      dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);
-      flash_attn_pp_kernel<<<grid2, PP_THREADS, PP_SMEM, st>>>(mq, mk, mv, p);
-    } break;
+#define PP_LAUNCH(POLY)                                                                                                          \
+  {                                                                                                                                \
+    static bool configured = false;                                                                                                \
+    if (!configured) {                                                                                                             \
+      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));       \
+      configured = true;                                                                                                           \
+    }                                                                                                                              \
+    dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
+    flash_attn_pp_kernel<POLY><<<grid2, PP_THREADS, PP_SMEM, st>>>(mq, mk, mv, p);                                                 \
+  }
+    case 10: PP_LAUNCH(4); break;    // ping-pong, 1/4 of the exponentials on the FMA pipe
+    case 11: PP_LAUNCH(2); break;    // ping-pong, 1/2
+    default: PP_LAUNCH(0); break;    // ping-pong: two query tiles per CTA, all exponentials on MUFU
+#undef PP_LAUNCH
   }
 #undef FA_LAUNCH
   B200_LAUNCH_OK();

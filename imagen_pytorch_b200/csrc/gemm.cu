@@ -9,7 +9,7 @@
 //                 B tiles are {64 k, BN n} boxes of the packed weights.  Both land 128B-swizzled.
 //   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16 bf16),
 //                 fp32 accumulator in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
-//   warps 2..5  : epilogue: tcgen05.ld (thread = output row, 64 consecutive columns in registers)
+//   warps 2..5 (2..9 for tiles of >= 128 columns): epilogue: tcgen05.ld (thread = output row, 16 columns at a time)
 //                 -> bias / SiLU / GELU / per-head L2 norm / residual / pixel-shuffle / NCHW fp32 stores.
 // Checker path (impl 1): a plain SIMT fp32 implicit GEMM + the same epilogue code, used only by tests
 // to isolate tensor-core/TMA descriptor bugs from epilogue/packing bugs.
@@ -21,7 +21,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_MAX_THREADS = 64 + 256;   // TMA warp + MMA warp + up to 8 epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
 struct SegDev {
@@ -270,7 +270,7 @@ __device__ __forceinline__ void tmem_wait_regs16(float* v) {
 // tile i+1.
 
 template <int BN, int STAGES, bool SIMPLE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * (BN >= 128 ? 8 : 4), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
@@ -303,7 +303,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], BN >= 128 ? 8 : 4);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -374,8 +374,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     }
   } else {
-    // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
+    // ---------------- epilogue warps: TMEM lane quarter = warp % 4.  Tiles of >= 128 columns get EIGHT epilogue warps (two per
+    // lane quarter, each owning half of the columns): epilogue-heavy GEMMs (small K, GELU, L2 norm) were bound by the four
+    // warps' instruction issue (ncu: FF1 with erf-GELU spent half its time in the epilogue math).
+    constexpr int HALVES = BN >= 128 ? 2 : 1;
+    constexpr int BNH = BN / HALVES;
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -384,8 +389,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const RowInfo ri = tile_row(p, tile, m);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
-      epilogue_row<BN, SIMPLE>(p, ri, n0, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
+      epilogue_row<BNH, SIMPLE>(p, ri, n0 + half * BNH, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
                        [&](float* v) { tmem_wait_regs16(v); });
       tc_fence_before();
       __syncwarp();
@@ -475,7 +480,7 @@ int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParam
   }
   const long long total = (long long)ntiles * (p.Npad / BN);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, GEMM_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, 64 + 32 * (BN >= 128 ? 8 : 4), smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }

@@ -110,13 +110,23 @@ class ElucidatedImagen(_SamplerBase):
                          lowres_noise_times=lowres_noise_times)
             chw = Cimg * H * W
             q_lo, q_hi, q_w = quantile_ranks(chw, self.dynamic_thresholding_percentile, device)
-            x = init_sigma * torch.randn(shape, device=device)                 # :442
-            x_hat, x1, d = (torch.empty_like(x) for _ in range(3))
-            eps = torch.empty_like(x)
+            st_ = plan.sampler_state.setdefault('edm', {})
+            if 'x' not in st_:
+                for name in ('x', 'x_hat', 'x1', 'd', 'eps'):
+                    st_[name] = torch.empty(shape, dtype=torch.float32, device=device)
+                st_['coefs'] = torch.empty((4096, 16), dtype=torch.float32, device=device)
+                st_['step_ctr'] = torch.zeros(2, dtype=torch.int32, device=device)
+                st_['graphs'] = {}
+            assert coefs.shape[0] <= 4096
+            x, x_hat, x1, d, eps, step_ctr = (st_[n] for n in ('x', 'x_hat', 'x1', 'd', 'eps', 'step_ctr'))
+            st_['coefs'][:coefs.shape[0]].copy_(coefs)
+            coefs = st_['coefs']
+            step_ctr.zero_()
+            x.copy_(init_sigma * torch.randn(shape, device=device))            # :442
             net_in = plan.x_in
-            step_ctr = torch.zeros(2, dtype=torch.int32, device=device)
             lib = plan.lib
             thr = int(bool(dynamic_threshold))
+            key = (float(cond_scale), thr, q_lo, q_hi, q_w)
 
             def phase(ph):
                 _lib.check(lib.b200_edm_phase(ph, x.data_ptr(), x_hat.data_ptr(), x1.data_ptr(), d.data_ptr(), net_in.data_ptr(),
@@ -147,14 +157,16 @@ class ElucidatedImagen(_SamplerBase):
                 except ImportError:
                     pass
             if _use_graph() and n_full > 1:
-                plan.launch()
-                torch.cuda.synchronize(device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    full_step()
+                graph = st_['graphs'].get(key)
+                if graph is None:
+                    plan.launch()
+                    torch.cuda.synchronize(device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        full_step()
+                    st_['graphs'][key] = graph
                 for _ in it:
                     graph.replay()
-                plan._last_graph = graph
             else:
                 for _ in it:
                     full_step()

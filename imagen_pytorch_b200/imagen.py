@@ -297,25 +297,34 @@ class Imagen(_SamplerBase):
             q_lo, q_hi, q_w = quantile_ranks(chw, self.dynamic_thresholding_percentile, device)
             x = plan.x_in
             x.copy_(torch.randn(shape, device=device))                         # :2195
-            noise = torch.empty(shape, dtype=torch.float32, device=device)
+            # persistent per-plan sampler buffers: the captured step graph bakes their addresses and is reused by later sample() calls
+            st_ = plan.sampler_state.setdefault('ddpm', {})
+            if 'noise' not in st_:
+                st_['noise'] = torch.empty(shape, dtype=torch.float32, device=device)
+                st_['coefs'] = torch.empty((plan.S, 8), dtype=torch.float32, device=device)
+                st_['graphs'] = {}
+            noise, coef_buf = st_['noise'], st_['coefs']
+            coef_buf[:T].copy_(coefs)
             lib = plan.lib
+            key = (float(cond_scale), objective, bool(dynamic_threshold), q_lo, q_hi, q_w)
 
             def one_step():
                 noise.copy_(torch.randn_like(x))                               # :2160 (drawn every step, also the last)
                 plan.launch()
                 st = torch.cuda.current_stream(device).cuda_stream
-                _lib.check(lib.b200_ddpm_step(x.data_ptr(), plan.pred.data_ptr(), noise.data_ptr(), coefs.data_ptr(), plan.slots.data_ptr(),
+                _lib.check(lib.b200_ddpm_step(x.data_ptr(), plan.pred.data_ptr(), noise.data_ptr(), coef_buf.data_ptr(), plan.slots.data_ptr(),
                                               R, B, chw, float(cond_scale), objective, int(bool(dynamic_threshold)), q_lo, q_hi, q_w, st),
                            'b200_ddpm_step')
 
-            self.last_launch_count = self._run_steps(one_step, T, plan, device, use_tqdm, launches_per_step=plan.n_launches + 2)
+            self.last_launch_count = self._run_steps(one_step, T, plan, device, use_tqdm, launches_per_step=plan.n_launches + 2,
+                                                     graph_cache=st_['graphs'], graph_key=key)
             out = torch.empty(shape, dtype=torch.float32, device=device)
             _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), int(self.auto_normalize_img),
                                                 torch.cuda.current_stream(device).cuda_stream), 'b200_finalize_images')   # :2281, :2288
         return out
 
     @staticmethod
-    def _run_steps(one_step, n_steps, plan, device, use_tqdm, launches_per_step):
+    def _run_steps(one_step, n_steps, plan, device, use_tqdm, launches_per_step, graph_cache=None, graph_key=None):
         it = range(n_steps)
         if use_tqdm:
             try:
@@ -324,14 +333,17 @@ class Imagen(_SamplerBase):
             except ImportError:
                 pass
         if _use_graph() and n_steps > 1:
-            plan.launch()                                                      # warm-up outside capture (lazy function attributes); touches no RNG
-            torch.cuda.synchronize(device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                one_step()
+            graph = graph_cache.get(graph_key) if graph_cache is not None else None
+            if graph is None:
+                plan.launch()                                                  # warm-up outside capture (lazy function attributes); touches no RNG
+                torch.cuda.synchronize(device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    one_step()
+                if graph_cache is not None:
+                    graph_cache[graph_key] = graph
             for _ in it:
                 graph.replay()
-            plan._last_graph = graph
         else:
             for _ in it:
                 one_step()

@@ -82,6 +82,7 @@ class UnetPlan:
         self.time_cond_table = self._zeros((n_slots, a.time_cond_dim), torch.float32)
         self.text_hiddens = self._zeros((R, a.time_cond_dim), torch.float32)
         self._scratch = None
+        self.sampler_state = {}      # persistent sampler buffers + captured step graphs (imagen.py / elucidated.py)
         self._build()
 
     # ------------------------------------------------------------------ small helpers

@@ -1,0 +1,15 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+OUT=gpurun_out
+PYT="python -m pytest -q --tb=short -p no:cacheprovider"
+timeout 900 $PYT tests/test_gpu_kernels.py -m gpu > $OUT/k_all.log 2>&1; echo "k_all $? $(tail -n1 $OUT/k_all.log)"; grep -E "^E " $OUT/k_all.log | head
+timeout 900 python - > $OUT/sweep_attn.log 2>&1 <<'PY'
+src = open('tools/sweep_attention.py').read().replace("for var in sorted(NAMES):", "for var in (9, 10, 11):")
+exec(compile(src, 'sweep', 'exec'))
+PY
+cat $OUT/sweep_attn.log
+timeout 1500 $PYT tests/test_gpu_unet.py -m gpu > $OUT/u_tc.log 2>&1; echo "u_tc $? $(tail -n1 $OUT/u_tc.log)"; grep -E "^E " $OUT/u_tc.log | head
+timeout 600 python bench.py --steps 2 --warmup 3 --timesteps 100 --no-cpu-baseline > $OUT/bench_100.log 2>&1; echo "bench100 $?"; grep '^{' $OUT/bench_100.log | cut -c1-200; grep -o '"roofline_conv".*' $OUT/bench_100.log | cut -c1-330
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv python tools/profile_step.py 2 16 > $OUT/prof_launch.log 2>&1; echo "ncu launches $? $(tail -n1 $OUT/prof_launch.log)"
+python tools/launch_summary.py $OUT/launches.csv 0 100 2>/dev/null | head -12
