@@ -29,7 +29,7 @@ constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
 constexpr int FA_MAX_SM_WARPS = 16;
-constexpr int FA_DEFAULT_VARIANT = 10;   // ping-pong, 1/4 of the exponentials on the FMA pipe (profiles/r01_attention_variant_sweep.txt)
+constexpr int FA_DEFAULT_VARIANT = 12;   // ping-pong with 16 softmax warps (profiles/r01_attention_variant_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
@@ -316,10 +316,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 constexpr int PP_THREADS = 384;
 constexpr int PP_STAGES = 4;                       // deep K/V ring: the two groups may drift apart by more than a tile
 constexpr int PP_PH_BYTES = FA_BM * 64 * 2;        // one 64-key half of a P tile (16 KB), its own full/empty barriers
-constexpr int PP_SMEM = 2 * FA_Q_BYTES + PP_STAGES * FA_KV_BYTES + 4 * PP_PH_BYTES + 1024 + 256;
+constexpr int PP_SMEM = 2 * FA_Q_BYTES + PP_STAGES * FA_KV_BYTES + 4 * PP_PH_BYTES + 1024 + 256;   // 230656 B of the 232448 B limit
 
-template <int POLY>   // every POLY-th exponential goes to the FMA pipe (0 = all on MUFU)
-__global__ void __launch_bounds__(PP_THREADS, 1)
+template <int POLY, int SUB>   // POLY: every POLY-th exponential goes to the FMA pipe (0 = all on MUFU); SUB: softmax warps per lane quarter per group
+__global__ void __launch_bounds__(128 + 256 * SUB, 1)
 flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t fa_smem_raw[];
@@ -351,9 +351,9 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     for (int s = 0; s < PP_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_empty[g], 128);
+      mbar_init(&s_empty[g], 128 * SUB);
       mbar_init(&o_full[g], 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }   // per 64-key half
+      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }   // per 64-key half (its 128 writer threads)
     }
     fence_barrier_init();
   }
@@ -428,8 +428,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       umma_commit(&o_full[g]);
     }
   } else if (warp >= 4) {
-    // ---------------- softmax / epilogue: group g, thread = query row of that group
-    const int g = (warp - 4) >> 2;
+    // ---------------- softmax / epilogue: group g, thread = (query row of that group, column half if SUB == 2).
+    // With SUB == 2 each scheduler sub-partition holds four softmax warps in four different phases (2 groups x 2 halves):
+    // the MUFU pipe of a sub-partition idles whenever all of its warps are in a TMEM-read / store / fence / barrier phase,
+    // which with only two warps per sub-partition happened ~45% of the time (XU pipe 55-59% in ncu).
+    const int idx = warp - 4;
+    const int g = idx / (4 * SUB);
+    const int sub = (idx >> 2) % SUB;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -440,58 +445,72 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       tc_fence_after();
       const int key0 = j * FA_BN;
       const bool ragged = key0 + FA_BN > p.n_keys;
-      // two halves of 64 score columns: 64 live registers instead of 128
+      // 64-key halves of the tile; a thread owns both (SUB == 1) or only half `sub` (SUB == 2).  Scores are pulled from TMEM
+      // in chunks of CH columns, load -> wait -> exponentiate (several tcgen05.ld in flight per warp are SLOWER:
+      // profiles/r01_tmem_ld_microbench.txt).
+      constexpr int CH = SUB == 2 ? 32 : 64;
 #pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t sr[64];
-        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64), sr);
-        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + 32), sr + 32);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
-        if (hf == 1) {
-          tc_fence_before();
-          mbar_arrive(&s_empty[g]);             // all of S_g is in registers: issuer g may start S_g(j+1)
-        }
+      for (int hh = 0; hh < 2 / SUB; ++hh) {
+        const int hf = SUB == 2 ? sub : hh;
         const int pb = 2 * g + hf;
         uint8_t* prow = sP + pb * PP_PH_BYTES + r * 128;
-        mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += CH) {
+          uint32_t sr[CH];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          uint32_t pk[4];
+          for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
-            float p1 = (POLY > 0 && ((8 * t + i + 1) % POLY) == POLY - 1) ? ex2_poly(__uint_as_float(sr[8 * t + i + 1]) - C)
-                                                                         : ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
-            if (ragged) {
-              if (key0 + hf * 64 + 8 * t + i >= p.n_keys) p0 = 0.f;
-              if (key0 + hf * 64 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
-            }
-            l += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < CH; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
+          if (c0 + CH == 64 && (SUB == 2 || hh == 1)) {
+            tc_fence_before();
+            mbar_arrive(&s_empty[g]);           // this thread's share of S_g is in registers
           }
-          *reinterpret_cast<uint4*>(prow + ((t ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (c0 == 0) mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half
+#pragma unroll
+          for (int t = 0; t < CH / 8; ++t) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
+              float p1 = (POLY > 0 && ((8 * t + i + 1) % POLY) == POLY - 1) ? ex2_poly(__uint_as_float(sr[8 * t + i + 1]) - C)
+                                                                           : ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
+              if (ragged) {
+                if (key0 + hf * 64 + c0 + 8 * t + i >= p.n_keys) p0 = 0.f;
+                if (key0 + hf * 64 + c0 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
+              }
+              l += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(prow + (((c0 / 8 + t) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive(&p_full[pb]);
       }
     }
-    // ---- O / l -> global
-    mbar_wait(&o_full[g], 0);
+    // ---- O / l -> global (with SUB == 2 the two column-half threads of a row add their sums and each stores 32 channels)
+    mbar_wait(&o_full[g], 0);                // every MMA of group g has completed: its P buffers are free
     tc_fence_after();
+    if (SUB == 2) {
+      float* sL = reinterpret_cast<float*>(sP + 2 * g * PP_PH_BYTES);   // [sub][128] partial row sums, in the group's own P buffer
+      sL[sub * FA_BM + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");         // the 8 softmax warps of this group
+      l = sL[r] + sL[FA_BM + r];
+    }
     const float inv = 1.f / l;
     const int row = row0 + g * FA_BM + r;
-    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs;
-    uint32_t orr[FA_D];
-    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + g * FA_D), orr);
-    tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + g * FA_D + 32), orr + 32);
+    constexpr int OC = FA_D / SUB;
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + sub * OC;
+    uint32_t orr[OC];
+#pragma unroll
+    for (int c = 0; c < OC; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + g * FA_D + sub * OC + c), orr + c);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < FA_D; ++i) asm volatile("" : "+r"(orr[i]));
+    for (int i = 0; i < OC; ++i) asm volatile("" : "+r"(orr[i]));
     if (row < p.rows) {
 #pragma unroll
-      for (int t = 0; t < FA_D / 8; ++t) {
+      for (int t = 0; t < OC / 8; ++t) {
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
         u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
@@ -579,19 +598,21 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 6: FA_LAUNCH(8, true, true); break;
     case 7: FA_LAUNCH(16, true, true); break;
     case 8: FA_LAUNCH(4, false, true); break;
-#define PP_LAUNCH(POLY)                                                                                                          \
+#define PP_LAUNCH(POLY, SUB)                                                                                                     \
   {                                                                                                                                \
     static bool configured = false;                                                                                                \
     if (!configured) {                                                                                                             \
-      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));       \
+      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel<POLY, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));  \
       configured = true;                                                                                                           \
     }                                                                                                                              \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
-    flash_attn_pp_kernel<POLY><<<grid2, PP_THREADS, PP_SMEM, st>>>(mq, mk, mv, p);                                                 \
+    flash_attn_pp_kernel<POLY, SUB><<<grid2, 128 + 256 * SUB, PP_SMEM, st>>>(mq, mk, mv, p);                                      \
   }
-    case 10: PP_LAUNCH(4); break;    // ping-pong, 1/4 of the exponentials on the FMA pipe
-    case 11: PP_LAUNCH(2); break;    // ping-pong, 1/2
-    default: PP_LAUNCH(0); break;    // ping-pong: two query tiles per CTA, all exponentials on MUFU
+    case 10: PP_LAUNCH(4, 1); break;   // ping-pong, 1/4 of the exponentials on the FMA pipe
+    case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
+    case 12: PP_LAUNCH(0, 2); break;   // ping-pong, 16 softmax warps (column halves)
+    case 13: PP_LAUNCH(4, 2); break;   // ... + 1/4 polynomial exp2
+    default: PP_LAUNCH(0, 1); break;   // ping-pong: two query tiles per CTA, all exponentials on MUFU
 #undef PP_LAUNCH
   }
 #undef FA_LAUNCH

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = {0: 'nw4', 1: 'nw8', 2: 'nw8+pf', 3: 'nw16', 4: 'nw16+pf', 5: 'nw8+wa', 6: 'nw8+pf+wa', 7: 'nw16+pf+wa', 8: 'nw4+wa', 9: 'pingpong', 10: 'pp+poly1/4', 11: 'pp+poly1/2'}
+NAMES = {0: 'nw4', 1: 'nw8', 2: 'nw8+pf', 3: 'nw16', 4: 'nw16+pf', 5: 'nw8+wa', 6: 'nw8+pf+wa', 7: 'nw16+pf+wa', 8: 'nw4+wa', 9: 'pingpong', 10: 'pp+poly1/4', 11: 'pp+poly1/2', 12: 'pp16', 13: 'pp16+poly1/4'}
 CODE = '''
 import sys, torch
 sys.path.insert(0, %r)
