@@ -8,11 +8,20 @@ namespace {
 constexpr int ROW_THREADS = 256;
 constexpr int MAX_VPT = 16;  // 16-byte vectors cached per thread -> C <= 32*16*8 = 4096
 
-// threads per row: aim at ~2 vectors (32 B) per thread so every thread has two independent loads in flight,
-// while small rows still fill the warp
+// threads per row: aim at ROW_TARGET_VPT vectors (16 B each) per thread so every thread has that many independent loads
+// in flight, while small rows still fill the warp (env B200_IMAGEN_ROW_VPT overrides the target for tuning sweeps)
+int row_target_vpt() {
+  static const int v = [] {
+    const char* e = getenv("B200_IMAGEN_ROW_VPT");
+    const int x = e ? atoi(e) : 0;
+    return (x == 1 || x == 2 || x == 4 || x == 8) ? x : 2;
+  }();
+  return v;
+}
 int pick_tpr(int vecs) {
+  const int target = row_target_vpt();
   int t = 1;
-  while (t * 4 <= vecs && t * 2 <= 32) t *= 2;
+  while (t * 2 * target <= vecs && t * 2 <= 32) t *= 2;
   return t;
 }
 int pick_vpt(int vecs, int tpr) {
@@ -20,6 +29,13 @@ int pick_vpt(int vecs, int tpr) {
   int v = 1;
   while (v < need) v *= 2;
   return v;
+}
+
+// 8 consecutive fp32 (32-byte aligned: every caller indexes at multiples of 8 from a cudaMalloc'd / 32 B-aligned base)
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 template <int TPR>
@@ -84,10 +100,13 @@ __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParam
       float f[8];
       unpack8(buf[i], f);
       const float sc = (c < p.C0 ? 1.f : p.scale1) * inv;
+      float g[8], fs[8], fb[8];
+      load8f(p.gamma + c, g);
+      if (film != nullptr) { load8f(film + c, fs); load8f(film + Ctot + c, fb); }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float y = f[j] * sc * __ldg(p.gamma + c + j);
-        if (film != nullptr) y = y * (__ldg(film + c + j) + 1.f) + __ldg(film + Ctot + c + j);
+        float y = f[j] * sc * g[j];
+        if (film != nullptr) y = y * (fs[j] + 1.f) + fb[j];
         f[j] = silu_f(y);
       }
       *reinterpret_cast<uint4*>(p.out + row * p.ldo + c) = pack8(f);
@@ -155,12 +174,11 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
       unpack8(buf[i], f);
       float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (p.residual != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + c)), r);
+      float g[8], be[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      load8f(p.g + c, g);
+      if (p.beta != nullptr) load8f(p.beta + c, be);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = (f[j] - mean) * rstd * __ldg(p.g + c + j);
-        if (p.beta != nullptr) y += __ldg(p.beta + c + j);
-        f[j] = y + r[j];
-      }
+      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[j] + be[j] + r[j];
       *reinterpret_cast<uint4*>(p.out + row * p.ldo + c) = pack8(f);
     }
   }
@@ -296,11 +314,15 @@ __global__ void __launch_bounds__(256) gca_mlp_kernel(const float* __restrict__ 
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
   const float* wr = W + (long long)n * K;
-  for (int k = lane; k < K; k += 32) {
-    const float w = __ldg(wr + k);
+#pragma unroll 2
+  for (int k = lane * 4; k < K; k += 128) {      // K % 4 == 0 (checked by the caller)
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
     for (int b = 0; b < MAXB; ++b)
-      if (b < B) acc[b] += w * __ldg(x + (long long)b * K + k);
+      if (b < B) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)b * K + k));
+        acc[b] += w.x * xv.x + w.y * xv.y + w.z * xv.z + w.w * xv.w;
+      }
   }
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) {
@@ -460,6 +482,8 @@ extern "C" int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1
   const int tpr = pick_tpr(vecs);
   const int vpt = pick_vpt(vecs, tpr);
   B200_REQUIRE(vpt <= MAX_VPT, "rmsnorm: C=%d too large", Ctot);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(gamma_sqrtC) & 15) == 0 && (film == nullptr || ((reinterpret_cast<uintptr_t>(film) & 15) == 0 && (film_ld & 3) == 0)),
+               "rmsnorm: gamma / film must be 16-byte aligned (film_ld %% 4 == 0)");
   DISPATCH_TPR(tpr, vpt, rmsnorm_film_silu_kernel, M, p);
   B200_LAUNCH_OK();
   return B200_OK;
@@ -478,6 +502,7 @@ extern "C" int b200_layernorm(const void* x, int32_t ldx, const float* g, const 
   const int tpr = pick_tpr(vecs);
   const int vpt = pick_vpt(vecs, tpr);
   B200_REQUIRE(vpt <= MAX_VPT, "layernorm: C=%d too large", C);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (beta == nullptr || (reinterpret_cast<uintptr_t>(beta) & 15) == 0), "layernorm: g / beta must be 16-byte aligned");
   DISPATCH_TPR(tpr, vpt, layernorm_kernel, M, p);
   B200_LAUNCH_OK();
   return B200_OK;
@@ -498,18 +523,21 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
   B200_REQUIRE((C & 7) == 0 && C <= 2048 && (ldx & 7) == 0, "gca: C=%d unsupported", C);
   B200_REQUIRE(nchunk >= 1 && B >= 1 && B <= 65535, "gca: bad nchunk/B");
   B200_REQUIRE((rows_per_sample + nchunk - 1) / nchunk <= GCA_MAX_CHUNK, "gca: chunk of %d pixels too large", (rows_per_sample + nchunk - 1) / nchunk);
-  // scratch layout: partials [B*nchunk*(C+2)] | pooled [B*C] | hidden [B*hidden] | logits [B*rows_per_sample]
-  float* pooled = scratch + (long long)B * nchunk * (C + 2);
+  B200_REQUIRE((hidden & 3) == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(w2) & 15) == 0, "gca: hidden %% 4 and 16-byte aligned scratch / weights required");
+  // scratch layout: pooled [B*C] | hidden [B*hidden] | partials [B*nchunk*(C+2)] | logits [B*rows_per_sample]
+  float* pooled = scratch;
   float* hid = pooled + (long long)B * C;
-  float* logits = hid + (long long)B * hidden;
+  float* partials = hid + (long long)B * hidden;
+  float* logits = partials + (long long)B * nchunk * (C + 2);
   const long long M = (long long)B * rows_per_sample;
   const int vecs = C >> 3;
   const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
   DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
   B200_LAUNCH_OK();
-  gca_pool_kernel<<<dim3(nchunk, B), GCA_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, scratch);
+  gca_pool_kernel<<<dim3(nchunk, B), GCA_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials);
   B200_LAUNCH_OK();
-  gca_combine_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(scratch, nchunk, C, pooled);
+  gca_combine_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(partials, nchunk, C, pooled);
   B200_LAUNCH_OK();
   const int bg = (B + 7) / 8;
   gca_mlp_kernel<8><<<dim3((hidden * 32 + 255) / 256, bg), 256, 0, st>>>(pooled, w1, b1, hid, B, hidden, C, 1);
