@@ -30,7 +30,8 @@ void b200_set_error(const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- small device helpers
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP (2 ulp) instead of the ~10-instruction IEEE division: every consumer rounds the result to bf16
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // exact-erf GELU (nn.GELU() default, imagen_pytorch.py:977).  erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far
 // below the bf16 output rounding) instead of erff(): ~12 FMA-pipe instructions + 2 MUFU instead of ~40 instructions --
 // the GEMM epilogue that applies it is issue-bound.
@@ -44,7 +45,7 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   const float erf_abs = 1.f - poly * t * __expf(-z * z);
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

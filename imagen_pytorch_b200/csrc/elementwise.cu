@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParam
   ss = group_sum<TPR>(ss);
   if (!active) return;
   const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  const float* film = p.film != nullptr ? p.film + (row / p.rows_per_sample) * (long long)p.film_ld : nullptr;
+  const float* film = p.film != nullptr ? p.film + (long long)((unsigned)row / (unsigned)p.rows_per_sample) * p.film_ld   /* M < 2^31 checked by the caller: 32-bit divide */ : nullptr;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = t + i * TPR;
@@ -342,7 +342,7 @@ __global__ void gate_residual_kernel(const __nv_bfloat16* __restrict__ x, int ld
   if (idx >= M * vecs) return;
   const long long row = idx / vecs;
   const int c = (int)(idx % vecs) << 3;
-  const int b = (int)(row / rows_per_sample);
+  const int b = (int)((unsigned)row / (unsigned)rows_per_sample);   // M < 2^31 (checked by the caller)
   float f[8], r[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * ldx + c)), f);
   unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * ldr + c)), r);
@@ -467,7 +467,7 @@ extern "C" int b200_rmsnorm_film_silu(const b200_src* srcs, int nsrc, float src1
                                       int32_t film_ld, int32_t rows_per_sample, void* out, int32_t ldo, int64_t M, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(nsrc == 1 || nsrc == 2, "rmsnorm: nsrc must be 1 or 2");
-  B200_REQUIRE(M > 0 && out && gamma_sqrtC, "rmsnorm: bad args");
+  B200_REQUIRE(M > 0 && M < (1ll << 31) && out && gamma_sqrtC, "rmsnorm: bad args");
   RmsParams p;
   p.src0 = reinterpret_cast<const __nv_bfloat16*>(srcs[0].ptr); p.C0 = srcs[0].C; p.ld0 = srcs[0].ld;
   p.src1 = nsrc == 2 ? reinterpret_cast<const __nv_bfloat16*>(srcs[1].ptr) : nullptr;
@@ -549,7 +549,7 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
 extern "C" int b200_gate_residual(const void* x, int32_t ldx, const float* gate, const void* residual, int32_t ldr, void* out, int32_t ldo,
                                   int64_t M, int32_t C, int32_t rows_per_sample, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  B200_REQUIRE(x && gate && residual && out, "gate_residual: null pointer");
+  B200_REQUIRE(x && gate && residual && out && M > 0 && M < (1ll << 31), "gate_residual: null pointer / bad M");
   B200_REQUIRE((C & 7) == 0 && (ldx & 7) == 0 && (ldr & 7) == 0 && (ldo & 7) == 0, "gate_residual: C/strides must be multiples of 8");
   const long long tot = M * (C >> 3);
   gate_residual_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, gate,

@@ -23,6 +23,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_MAX_THREADS = 64 + 256;   // TMA warp + MMA warp + up to 8 epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int EPI_STAGE_BYTES = 2048 + 512;   // per epilogue warp: 32 rows x 64 B staging tile + 32 x 16 B row metadata
 
 struct SegDev {
   int8_t src, dh, dw, pad;
@@ -41,9 +42,12 @@ struct EpiDev {
 struct GemmParams {
   int B, H, W;
   int bw, bh, bb;
+  int lbw, lbh;   // log2(bw), log2(bh)
   int tiles_w, tiles_h;
   int N, Npad;
   int nseg, total_chunks, ntiles_m;
+  int tma_store;   // staged epilogue hands each 32-row x 32-column group to a TMA store (plain bf16 row-major destinations)
+  int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads
   int nchunks[B200_MAX_SRC];
   SegDev seg[B200_MAX_SEG];
   EpiDev epi;
@@ -58,15 +62,28 @@ struct RowInfo {
   long long orow;  // after the optional row remap
 };
 
-__device__ __forceinline__ RowInfo tile_row(const GemmParams& p, int tile, int m) {
-  const int wblk = tile % p.tiles_w;
-  const int hblk = (tile / p.tiles_w) % p.tiles_h;
-  const int bblk = tile / (p.tiles_w * p.tiles_h);
-  const int lw = m % p.bw, lh = (m / p.bw) % p.bh, lb = m / (p.bw * p.bh);
+// position of accumulator row m inside the tile box (constant per thread): bw / bh are powers of two
+struct RowInTile {
+  int lw, lh, lb;
+};
+__device__ __forceinline__ RowInTile row_in_tile(const GemmParams& p, int m) {
+  RowInTile r;
+  r.lw = m & (p.bw - 1);
+  r.lh = (m >> p.lbw) & (p.bh - 1);
+  r.lb = m >> (p.lbw + p.lbh);
+  return r;
+}
+
+__device__ __forceinline__ RowInfo tile_row(const GemmParams& p, int tile, const RowInTile& t) {
+  const unsigned ut = (unsigned)tile;
+  const unsigned tq = ut / (unsigned)p.tiles_w;
+  const int wblk = (int)(ut - tq * (unsigned)p.tiles_w);
+  const unsigned bblk = tq / (unsigned)p.tiles_h;
+  const int hblk = (int)(tq - bblk * (unsigned)p.tiles_h);
   RowInfo r;
-  r.w = wblk * p.bw + lw;
-  r.h = hblk * p.bh + lh;
-  r.b = bblk * p.bb + lb;
+  r.w = wblk * p.bw + t.lw;
+  r.h = hblk * p.bh + t.lh;
+  r.b = (int)bblk * p.bb + t.lb;
   r.valid = (r.w < p.W) && (r.h < p.H) && (r.b < p.B);
   r.row = ((long long)r.b * p.H + r.h) * p.W + r.w;
   r.orow = r.row;
@@ -257,6 +274,238 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, const RowInfo&
   }
 }
 
+// ---- staged epilogue (product path for every bf16 output mode) --------------------------------------------------------
+// The TMEM layout gives each thread one output ROW, so direct stores scatter every warp instruction over 32 rows (32
+// half-used sectors; tools/gemm_bench.py measured the small-K linears 3-5x slower with the epilogue than without).  Each
+// epilogue warp therefore owns a 32-row x 64-column (128 B) staging tile in shared memory, XOR-swizzled in 16 B chunks:
+//   phase A (thread = row): tcgen05.ld 16 columns at a time -> bias/act/scale -> bf16 -> st.shared      (conflict free)
+//   phase B (8 lanes = one row): ld.shared 16 B -> [L2-norm scale] [+ residual] -> st.global: every warp instruction writes
+//            four complete 128 B lines.
+// Per-row data (destination, validity, 1/norm, residual row) travel from the row's owner lane by shuffle.
+// bf16 destinations only; a 64-column group never straddles a destination switch (split_col % 64 == 0, ps_C % 64 == 0).
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// where column n (a multiple of 64) of this row goes, and the row pitch of that destination
+__device__ __forceinline__ __nv_bfloat16* bf16_group_dst(const GemmParams& p, const RowInfo& ri, int n, int& ld) {
+  const EpiDev& e = p.epi;
+  if (e.out_mode == B200_OUT_PIXEL_SHUFFLE) {
+    const int r = n / e.ps_C, c = n - r * e.ps_C;
+    const long long prow = ((long long)ri.b * (2 * p.H) + 2 * ri.h + (r >> 1)) * (2 * p.W) + 2 * ri.w + (r & 1);
+    ld = e.ldc;
+    return reinterpret_cast<__nv_bfloat16*>(e.out) + prow * e.ldc + c;
+  }
+  if (e.split_col > 0 && n >= e.split_col) {
+    ld = e.ldc2;
+    return reinterpret_cast<__nv_bfloat16*>(e.out2) + ri.orow * (long long)e.ldc2 + (n - e.split_col);
+  }
+  ld = e.ldc;
+  return reinterpret_cast<__nv_bfloat16*>(e.out) + ri.orow * (long long)e.ldc + n;
+}
+
+// bias + activation + scale on 32 consecutive columns starting at n (branches are warp-uniform)
+__device__ __forceinline__ void epi_math32(const EpiDev& e, int n, float* v) {
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n + j));
+      v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    }
+  }
+  if (e.act == B200_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+  } else if (e.act == B200_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+  }
+  if (e.out_scale != 1.f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= e.out_scale;
+  }
+}
+
+// phase A for 32 columns: the thread's row of the 32-row x 64-byte staging tile (16-byte chunks XOR-swizzled so that both the
+// row-wise writes here and the 4-lanes-per-row reads of flush32 are bank-conflict free)
+__device__ __forceinline__ void stage32(const float* v, uint32_t stage, int lane) {
+  const uint32_t rowaddr = stage + (uint32_t)lane * 64u;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_shared_v4(rowaddr + (uint32_t)((i ^ sw) << 4), pack8(v + 8 * i));
+}
+
+// phase B for 32 columns starting at ng: 4 lanes = one row (64 contiguous bytes), 8 rows per warp instruction
+__device__ __forceinline__ void flush32(const GemmParams& p, const RowInfo& ri, int ng, uint32_t stage, uint32_t meta, int lane) {
+  const EpiDev& e = p.epi;
+  int ld;
+  __nv_bfloat16* dst = bf16_group_dst(p, ri, ng, ld);
+  const long long my_dst = ri.valid ? reinterpret_cast<long long>(dst) : 0ll;
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(meta + (uint32_t)lane * 16u), "r"((uint32_t)my_dst), "r"((uint32_t)(my_dst >> 32)),
+               "r"((uint32_t)ri.row), "r"(0u)
+               : "memory");
+  const int rs = lane >> 2, ch = lane & 3;
+  const int col = ng + ch * 8;
+  const uint32_t rd = stage + (uint32_t)rs * 64u + (uint32_t)((ch ^ ((rs >> 1) & 3)) << 4);   // + 512 per 8 rows; (row >> 1) & 3 == (rs >> 1) & 3
+  __syncwarp();
+  uint4 u[4];
+  uint32_t m0[4], m1[4], m2[4], m3[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    u[r] = ld_shared_v4(rd + (uint32_t)r * 512u);
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0[r]), "=r"(m1[r]), "=r"(m2[r]), "=r"(m3[r]) : "r"(meta + (uint32_t)(8 * r + rs) * 16u) : "memory");
+  }
+  if (col < p.N) {
+    if (e.residual != nullptr) {
+      uint4 rr[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        rr[r] = make_uint4(0u, 0u, 0u, 0u);
+        if ((m0[r] | m1[r]) != 0u) rr[r] = __ldg(reinterpret_cast<const uint4*>(e.residual + (long long)(int)m2[r] * e.ldr + col));
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float f[8], g[8];
+        unpack8(u[r], f);
+        unpack8(rr[r], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += g[j];
+        u[r] = pack8(f);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long d = (long long)(((unsigned long long)m1[r] << 32) | m0[r]);
+      if (d != 0) {
+        __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(d) + ch * 8;
+        *reinterpret_cast<uint4*>(q) = u[r];
+        if (e.dup_rows > 0) *reinterpret_cast<uint4*>(q + (long long)e.dup_rows * ld) = u[r];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Straight-line code on purpose: the epilogue runs on 8 warps (2 per scheduler), so it is bound by dependent-instruction
+// latency, not issue slots (ncu on the K=128 linears: CPI 6 per warp with a rolled 16-column loop).  One tcgen05.ld.x32 per
+// wait, the next one in flight while 32 columns are converted, and all row reads of a flush issued together.
+// hand the staged 32 x 32 group to the TMA engine: the async proxy reads the tile after the fence; OOB rows / columns are clipped
+__device__ __forceinline__ void flush32_tma(const CUtensorMap* mapO, const RowInfo& ri, int ng, uint32_t stage, int lane) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {   // lane 0 owns the first row of the warp's 32: its (w, h, b) are the box origin
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(mapO), "r"(stage), "r"(ng), "r"(ri.w),
+                 "r"(ri.h), "r"(ri.b)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+// the staging tile may be rewritten once the previous store has finished READING it
+__device__ __forceinline__ void tma_store_wait_read(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
+template <int BNW, class Load32, class Wait32>
+__device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUtensorMap* mapO, const RowInfo& ri, int n0, uint32_t stage, uint32_t meta,
+                                                int lane, Load32 load32, Wait32 wait32) {
+  static_assert(BNW % 32 == 0, "staged epilogue works on 32-column groups");
+  const EpiDev& e = p.epi;
+  float va[32], vb[32];
+  if (e.l2_cols > 0) {
+    // F.normalize over 64-column heads: pass 1 = sum of squares of the activated values, pass 2 = reload, scale, stage.
+    // (the scale is applied in fp32 before the single bf16 rounding)
+#pragma unroll 1
+    for (int g0 = 0; g0 < BNW; g0 += 64) {
+      const int ng = n0 + g0;
+      if (ng >= p.N) break;
+      const bool l2 = ng < e.l2_cols;
+      float inv = 1.f;
+      if (l2) {
+        float ss = 0.f;
+#pragma unroll 1
+        for (int h = 0; h < 64 && h < BNW; h += 32) {
+          load32(g0 + h, va);
+          wait32(va);
+          epi_math32(e, ng + h, va);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ss += va[j] * va[j];
+        }
+        inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      }
+#pragma unroll 1
+      for (int h = 0; h < 64 && h < BNW; h += 32) {
+        if (ng + h >= p.N) break;
+        load32(g0 + h, va);
+        wait32(va);
+        epi_math32(e, ng + h, va);
+        if (l2) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (e.l2_scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(e.l2_scale + h + j));
+            va[j] *= inv * s4.x; va[j + 1] *= inv * s4.y; va[j + 2] *= inv * s4.z; va[j + 3] *= inv * s4.w;
+          }
+        }
+        if (p.tma_store) {
+          tma_store_wait_read(lane);
+          stage32(va, stage, lane);
+          flush32_tma(mapO, ri, ng + h, stage, lane);
+        } else {
+          stage32(va, stage, lane);
+          flush32(p, ri, ng + h, stage, meta, lane);
+        }
+      }
+    }
+    return;
+  }
+  load32(0, va);
+#pragma unroll 1
+  for (int g0 = 0; g0 < BNW; g0 += 64) {
+    const int ng = n0 + g0;
+    if (ng >= p.N) break;
+    wait32(va);
+    if (g0 + 32 < BNW) load32(g0 + 32, vb);
+    epi_math32(e, ng, va);
+    if (p.tma_store) {
+      tma_store_wait_read(lane);
+      stage32(va, stage, lane);
+      flush32_tma(mapO, ri, ng, stage, lane);
+    } else {
+      stage32(va, stage, lane);
+      flush32(p, ri, ng, stage, meta, lane);
+    }
+    if (g0 + 32 < BNW && ng + 32 < p.N) {
+      wait32(vb);
+      if (g0 + 64 < BNW) load32(g0 + 64, va);
+      epi_math32(e, ng + 32, vb);
+      if (p.tma_store) {
+        tma_store_wait_read(lane);
+        stage32(vb, stage, lane);
+        flush32_tma(mapO, ri, ng + 32, stage, lane);
+      } else {
+        stage32(vb, stage, lane);
+        flush32(p, ri, ng + 32, stage, meta, lane);
+      }
+    } else if (g0 + 32 < BNW) {
+      wait32(vb);   // drain the prefetch before leaving
+    }
+  }
+  tmem_ld_wait();   // a prefetch may still be in flight when the column loop ends at N: never release the accumulator under it
+}
+
+__device__ __forceinline__ void tmem_wait_regs32(float* v) {
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) asm volatile("" : "+f"(v[i]));
+}
+
 // wait::ld, then pin the 16 destination registers behind the wait so the compiler cannot hoist their uses above it
 __device__ __forceinline__ void tmem_wait_regs16(float* v) {
   tmem_ld_wait();
@@ -269,11 +518,11 @@ __device__ __forceinline__ void tmem_wait_regs16(float* v) {
 // tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 
-template <int BN, int STAGES, bool SIMPLE>
+template <int BN, int STAGES, bool STAGED>
 __global__ void __launch_bounds__(64 + 32 * (BN >= 128 ? 8 : 4), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO, const __grid_constant__ GemmParams p) {
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -297,6 +546,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     if (p.nchunks[2] > 0) tma_prefetch_desc(&mapA2);
     if (p.nchunks[3] > 0) tma_prefetch_desc(&mapA3);
     tma_prefetch_desc(&mapB);
+    if (STAGED && p.tma_store) tma_prefetch_desc(&mapO);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -334,10 +584,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            uint8_t* sA = smem + stage * STAGE_BYTES;
-            tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
-            tma_load_2d(sA + A_TILE_BYTES, &mapB, &full_bar[stage], kc * BK, n0);
+            if (p.debug & 4) {
+              mbar_arrive(&full_bar[stage]);
+            } else {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              uint8_t* sA = smem + stage * STAGE_BYTES;
+              tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+              tma_load_2d(sA + A_TILE_BYTES, &mapB, &full_bar[stage], kc * BK, n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -360,10 +614,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
           const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -381,17 +637,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     constexpr int BNH = BN / HALVES;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int m = q * 32 + lane;
+    const RowInTile rit = row_in_tile(p, q * 32 + lane);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int tile = t / n_tiles_n, n0 = (t % n_tiles_n) * BN;
-      const RowInfo ri = tile_row(p, tile, m);
+      const int tile = (int)((unsigned)t / (unsigned)n_tiles_n), n0 = (t - tile * n_tiles_n) * BN;
+      const RowInfo ri = tile_row(p, tile, rit);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
-      epilogue_row<BNH, SIMPLE>(p, ri, n0 + half * BNH, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
-                       [&](float* v) { tmem_wait_regs16(v); });
+      if (!(p.debug & 1)) {
+        if constexpr (STAGED) {
+          const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
+          epilogue_staged<BNH>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
+                               [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                               [&](float* v) { tmem_wait_regs32(v); });
+        } else {
+          epilogue_row<BNH, false>(p, ri, n0 + half * BNH, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                                   [&](float* v) { tmem_wait_regs16(v); });
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -399,10 +664,173 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       if (acc == 0) acc_phase ^= 1u;
     }
   }
+  if (STAGED && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // TMA stores read this CTA's shared memory
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tcgen05 kernel, CTA pairs
+// Same pipeline with cta_group::2: the two CTAs of a 2-wide cluster (one TPC) compute one 256 x BN tile.  Each CTA loads
+// the A tile of ITS 128 output rows and HALF of the B tile (BN/2 weight rows); the rank-0 CTA issues M=256 MMAs that read
+// both shared memories and write each CTA's 128 accumulator lanes.  Per 128 x BN of output a CTA therefore pulls
+// 16 KB + BN*64 B per K chunk instead of 16 KB + BN*128 B -- the conv GEMMs are bound by L2->SM operand traffic
+// (profiles/r01_ncu_conv_gemm_summary.txt), so this is where the time goes.
+//   full[s]   (rank 0 only): 1 arrival (rank 0's expect_tx of BOTH CTAs' bytes) + the TMA bytes of both CTAs
+//   empty[s]  (both CTAs)  : multicast tcgen05.commit -> each producer waits locally
+//   tmem_full (both CTAs)  : multicast tcgen05.commit -> each CTA's epilogue warps wait locally
+//   tmem_empty (rank 0)    : 8 epilogue warps x 2 CTAs arrive (remote arrive from rank 1)
+
+template <int BN, int STAGES, bool STAGED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO, const __grid_constant__ GemmParams p) {
+  constexpr int BNH = BN / 2;                       // B rows held by one CTA == columns owned by one epilogue half
+  constexpr int B_TILE_BYTES = BNH * BK * 2;
+  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;                 // two accumulator stages
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tiles_n = p.Npad / BN;
+  const int npairs_m = (p.ntiles_m + 1) / 2;
+  const int total_tiles = npairs_m * n_tiles_n;
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.nchunks[1] > 0) tma_prefetch_desc(&mapA1);
+    if (p.nchunks[2] > 0) tma_prefetch_desc(&mapA2);
+    if (p.nchunks[3] > 0) tma_prefetch_desc(&mapA3);
+    tma_prefetch_desc(&mapB);
+    if (STAGED && p.tma_store) tma_prefetch_desc(&mapO);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 16);   // 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, (uint32_t)TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();                      // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair0; t < total_tiles; t += pair_stride) {
+        const int tile = 2 * (t / n_tiles_n) + (int)rank, n0 = (t % n_tiles_n) * BN + (int)rank * BNH;
+        const int wblk = tile % p.tiles_w;
+        const int hblk = (tile / p.tiles_w) % p.tiles_h;
+        const int bblk = tile / (p.tiles_w * p.tiles_h);   // tile == ntiles_m (odd tile count): b0 >= B, TMA zero-fills
+        const int w0 = wblk * p.bw, h0 = hblk * p.bh, b0 = bblk * p.bb;
+        int kc = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int src = p.seg[s].src;
+          const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : (src == 2 ? &mapA2 : &mapA3));
+          const int dh = p.seg[s].dh, dw = p.seg[s].dw;
+          const int nch = p.nchunks[src];
+          for (int cc = 0; cc < nch; ++cc, ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (p.debug & 4) {
+              if (rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              const uint32_t full0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              uint8_t* sA = smem + stage * STAGE_BYTES;
+              tma_load_4d_2sm(sA, mA, full0, cc * BK, w0 + dw, h0 + dh, b0);
+              tma_load_2d_2sm(sA + A_TILE_BYTES, &mapB, full0, kc * BK, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (rank 0 only): M = 256 over the pair, N = BN
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = pair0; t < total_tiles; t += pair_stride) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kc = 0; kc < p.total_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+          if (!(p.debug & 2)) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (both CTAs): lane quarter = warp % 4, column half = (warp - 2) / 4
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const RowInTile rit = row_in_tile(p, q * 32 + lane);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair0; t < total_tiles; t += pair_stride) {
+      const int tq = (int)((unsigned)t / (unsigned)n_tiles_n);
+      const int tile = 2 * tq + (int)rank, n0 = (t - tq * n_tiles_n) * BN;
+      const RowInfo ri = tile_row(p, tile, rit);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * BNH);
+      if (!(p.debug & 1)) {
+        if constexpr (STAGED) {
+          const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
+          epilogue_staged<BNH>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
+                               [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                               [&](float* v) { tmem_wait_regs32(v); });
+        } else {
+          epilogue_row<BNH, false>(p, ri, n0 + half * BNH, [&](int c, float* v) { tmem_ld16_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                                   [&](float* v) { tmem_wait_regs16(v); });
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  if (STAGED && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // TMA stores read this CTA's shared memory
+  tc_fence_before();
+  cluster_sync_all();                      // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, (uint32_t)TMEM_COLS);
   }
 }
 
@@ -471,8 +899,9 @@ int next_pow2(int v) {
 }
 
 template <int BN, int STAGES, bool SIMPLE>
-int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams& p, int ntiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + (BN >= 128 ? 8 : 4) * EPI_STAGE_BYTES : 0) /*staging*/;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -480,18 +909,60 @@ int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParam
   }
   const long long total = (long long)ntiles * (p.Npad / BN);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, 64 + 32 * (BN >= 128 ? 8 : 4), smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, 64 + 32 * (BN >= 128 ? 8 : 4), smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+// every bf16 destination with 16-byte-aligned 8-column chunks takes the staged (coalescing) epilogue; the rest (fp32 outputs,
+// odd channel counts, < 64 columns) keep the per-thread-row epilogue
+bool gemm_is_simple(const GemmParams& p) {
+  const EpiDev& e = p.epi;
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!(e.out_mode == B200_OUT_BF16 || e.out_mode == B200_OUT_PIXEL_SHUFFLE)) return false;
+  if (p.Npad < 64 || (p.N & 7) != 0 || (e.ldc & 7) != 0 || !al16(e.out)) return false;
+  if (e.out_mode == B200_OUT_PIXEL_SHUFFLE && (e.ps_C % 64 != 0 || e.split_col != 0)) return false;
+  if (e.split_col > 0 && ((e.ldc2 & 7) != 0 || !al16(e.out2))) return false;
+  if (e.residual != nullptr && ((e.ldr & 7) != 0 || !al16(e.residual))) return false;
+  if (e.dup_rows > 0 && e.split_col > 0) return false;
+  if (e.l2_scale != nullptr && !al16(e.l2_scale)) return false;
+  return (long long)p.B * p.H * p.W < (1ll << 31);
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
+  return gemm_is_simple(p) ? launch_tc2<BN, STAGES, true>(maps, mapB, mapO, p, ntiles, st) : launch_tc2<BN, STAGES, false>(maps, mapB, mapO, p, ntiles, st);
+}
+
+template <int BN, int STAGES, bool SIMPLE>
+int launch_pair2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_TILE_BYTES + (BN / 2) * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + 8 * EPI_STAGE_BYTES : 0) /*staging*/;
+  static_assert(smem <= 232448, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, STAGES, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const long long total = (long long)((ntiles + 1) / 2) * (p.Npad / BN);     // 256 x BN tiles
+  const int pairs = (int)(total < sm_count() / 2 ? total : sm_count() / 2);  // persistent: one CTA pair per TPC
+  conv_gemm_tc2_kernel<BN, STAGES, SIMPLE><<<2 * pairs, 64 + 256, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }
 
 template <int BN, int STAGES>
-int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const GemmParams& p, int ntiles, cudaStream_t st) {
-  const EpiDev& e = p.epi;
-  const bool simple = e.out_mode == B200_OUT_BF16 && e.split_col == 0 && e.rows_per_group == 0 && e.dup_rows == 0 && e.l2_cols == 0 &&
-                      (p.N & 15) == 0 && (e.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 &&
-                      (e.residual == nullptr || ((e.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0));
-  return simple ? launch_tc2<BN, STAGES, true>(maps, mapB, p, ntiles, st) : launch_tc2<BN, STAGES, false>(maps, mapB, p, ntiles, st);
+int launch_pair(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
+  return gemm_is_simple(p) ? launch_pair2<BN, STAGES, true>(maps, mapB, mapO, p, ntiles, st) : launch_pair2<BN, STAGES, false>(maps, mapB, mapO, p, ntiles, st);
+}
+
+// B200_IMAGEN_GEMM_PAIR=1 routes the GEMMs with >= 128 columns to the CTA-pair kernel.  Off by default: on B200 it measured
+// ~10 % slower than the single-CTA kernel on every shape of the workload (profiles/r01_gemm_bottleneck.txt).
+bool pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_IMAGEN_GEMM_PAIR");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
 }
 
 }  // namespace
@@ -516,6 +987,10 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   p.N = N;
   p.Npad = b200_conv_gemm_npad(N);
   p.nseg = nseg;
+  {
+    static const int dbg = [] { const char* e = getenv("B200_IMAGEN_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
+  }
   for (int i = 0; i < nsrc; ++i) {
     B200_REQUIRE(srcs[i].ptr != nullptr && srcs[i].C > 0, "conv_gemm: src %d empty", i);
     B200_REQUIRE((srcs[i].ld & 7) == 0 && srcs[i].ld >= srcs[i].C, "conv_gemm: src %d ld=%d must be a multiple of 8 and >= C=%d", i, srcs[i].ld, srcs[i].C);
@@ -535,6 +1010,8 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   p.bw = W >= 128 ? 128 : next_pow2(W);
   p.bh = next_pow2(H) < 128 / p.bw ? next_pow2(H) : 128 / p.bw;
   p.bb = 128 / (p.bw * p.bh);
+  for (p.lbw = 0; (1 << p.lbw) < p.bw; ++p.lbw) {}
+  for (p.lbh = 0; (1 << p.lbh) < p.bh; ++p.lbh) {}
   p.tiles_w = (W + p.bw - 1) / p.bw;
   p.tiles_h = (H + p.bh - 1) / p.bh;
   const int tiles_b = (B + p.bb - 1) / p.bb;
@@ -583,10 +1060,14 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   // ---- tensor maps
   EncodeTiledFn enc = get_encode_fn();
   B200_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled not available from the driver");
+  // tile shape: CTA pairs (256 x BN per pair, B split across the pair) whenever there are >= 2 row tiles and >= 128 columns
+  const bool pair = pair_enabled() && ntiles >= 2 && p.Npad >= 128;
   int BN;
   if (p.Npad <= 64) BN = p.Npad;
+  else if (pair) BN = (p.Npad % 256 == 0 && (long long)((ntiles + 1) / 2) * (p.Npad / 256) >= sm_count() / 2) ? 256 : 128;
   else if (p.Npad % 256 == 0 && (long long)ntiles * (p.Npad / 256) >= sm_count()) BN = 256;   // wide tiles only if they still fill the chip
   else BN = 128;
+  const int boxN = pair ? BN / 2 : BN;
   CUtensorMap maps[B200_MAX_SRC];
   memset(maps, 0, sizeof(maps));
   for (int i = 0; i < nsrc; ++i) {
@@ -605,18 +1086,40 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)boxN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (Ktot=%d Npad=%d BN=%d)", (int)r, Ktot, p.Npad, BN);
   }
+  // output map for the TMA-store epilogue: plain bf16 row-major destination, nothing but bias / activation / scale / L2 norm
+  CUtensorMap mapO = mapB;
+  p.tma_store = 0;
+  {
+    static const bool tma_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_TMA_STORE"); return ev == nullptr || atoi(ev) != 0; }();
+    if (tma_on && gemm_is_simple(p) && e.out_mode == B200_OUT_BF16 && e.residual == nullptr && e.split_col == 0 && e.rows_per_group == 0 &&
+        e.dup_rows == 0 && (((long long)e.ldc * 2) & 15) == 0) {
+      // the 32 rows of one epilogue warp are a sub-box of the tile box {bw, bh, bb}
+      const int sw_ = p.bw < 32 ? p.bw : 32;
+      const int sh_ = (32 / sw_) < p.bh ? (32 / sw_) : p.bh;
+      const int sb_ = 32 / (sw_ * sh_);
+      cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)e.ldc * 2, (cuuint64_t)e.ldc * 2 * W, (cuuint64_t)e.ldc * 2 * W * H};
+      cuuint32_t box[4] = {32u, (cuuint32_t)sw_, (cuuint32_t)sh_, (cuuint32_t)sb_};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, e.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(out) failed with %d (N=%d ldc=%d W=%d H=%d B=%d)", (int)r, N, e.ldc, W, H, B);
+      p.tma_store = 1;
+    }
+  }
+  if (pair) return BN == 256 ? launch_pair<256, 6>(maps, mapB, mapO, p, ntiles, st) : launch_pair<128, 8>(maps, mapB, mapO, p, ntiles, st);
   switch (BN) {
     // persistent, one CTA per SM: the whole 227 KB of shared memory goes to the operand ring
-    case 32: return launch_tc<32, 8>(maps, mapB, p, ntiles, st);
-    case 64: return launch_tc<64, 8>(maps, mapB, p, ntiles, st);
-    case 128: return launch_tc<128, 6>(maps, mapB, p, ntiles, st);
-    default: return launch_tc<256, 4>(maps, mapB, p, ntiles, st);
+    case 32: return launch_tc<32, 8>(maps, mapB, mapO, p, ntiles, st);
+    case 64: return launch_tc<64, 8>(maps, mapB, mapO, p, ntiles, st);
+    case 128: return launch_tc<128, 6>(maps, mapB, mapO, p, ntiles, st);
+    default: return launch_tc<256, 4>(maps, mapB, mapO, p, ntiles, st);
   }
 }

@@ -67,6 +67,8 @@ class GemmCall:
         e.l2_scale = l2_scale.data_ptr() if l2_scale is not None else None
         e.ps_C, e.dup_rows = ps_C, dup_rows
         self.e = e
+        self.desc = {'B': grid[0], 'H': grid[1], 'W': grid[2], 'N': N, 'nseg': len(segs), 'C': [c for (_, c, _) in srcs],
+                     'K': sum(-(-srcs[g[0]][1] // 64) * 64 for g in segs), 'act': act, 'out_mode': out_mode}
         self.args = (self.sa, len(srcs), self.ga, len(segs), grid[0], grid[1], grid[2], wpacked.data_ptr(), N, C.byref(e), impl, scratch_ptr)
 
     def __call__(self, stream):

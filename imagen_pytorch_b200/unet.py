@@ -434,6 +434,10 @@ class UnetPlan:
         self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4
 
     # ------------------------------------------------------------------ execution
+    def describe_gemms(self):
+        """[{B,H,W,N,K,...}] of every b200_conv_gemm launch of one evaluation, in launch order (profiling aid)."""
+        return [c.desc for c in self._keep if isinstance(c, ops.GemmCall)]
+
     def launch(self, stream=None):
         """Enqueue one U-Net evaluation (x_in -> pred) on the current stream. CUDA-graph capturable."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream

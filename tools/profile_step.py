@@ -16,3 +16,7 @@ torch.manual_seed(0)
 out = im.sample(text_embeds=torch.randn(bs, 256, 768, device='cuda'), cond_scale=3., use_tqdm=False)
 torch.cuda.synchronize()
 print('ok', out.shape, im.last_launch_count)
+import json
+plan = next(iter(im.unets[0]._plans.values()))
+os.makedirs('gpurun_out', exist_ok=True)
+json.dump(plan.describe_gemms(), open('gpurun_out/plan_gemms.json', 'w'))
