@@ -78,6 +78,8 @@ SIGNATURES = {
     'b200_headnorm_store': [_P, _I, _I, _I, _I, _P, _P, _I, _L, _L, _L, _L, _P],
     'b200_ddpm_step': [_P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _I, _F, _P],
     'b200_edm_phase': [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _F, _P],
+    'b200_inpaint_mix': [_P, _P, _P, _P, _F, _F, _I, _I, _L, _P],
+    'b200_renoise': [_P, _P, _F, _F, _F, _L, _P],
     'b200_finalize_images': [_P, _P, _L, _I, _P],
 }
 

@@ -47,7 +47,7 @@ struct GemmParams {
   int N, Npad;
   int nseg, total_chunks, ntiles_m;
   int tma_store;   // staged epilogue hands each 32-row x 32-column group to a TMA store (plain bf16 row-major destinations)
-  int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads
+  int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads, 8 no wait before restaging (WRONG results), 16 no proxy fence (WRONG results)
   int nchunks[B200_MAX_SRC];
   SegDev seg[B200_MAX_SEG];
   EpiDev epi;
@@ -396,8 +396,8 @@ __device__ __forceinline__ void flush32(const GemmParams& p, const RowInfo& ri, 
 // latency, not issue slots (ncu on the K=128 linears: CPI 6 per warp with a rolled 16-column loop).  One tcgen05.ld.x32 per
 // wait, the next one in flight while 32 columns are converted, and all row reads of a flush issued together.
 // hand the staged 32 x 32 group to the TMA engine: the async proxy reads the tile after the fence; OOB rows / columns are clipped
-__device__ __forceinline__ void flush32_tma(const CUtensorMap* mapO, const RowInfo& ri, int ng, uint32_t stage, int lane) {
-  fence_proxy_async_smem();
+__device__ __forceinline__ void flush32_tma(const CUtensorMap* mapO, const RowInfo& ri, int ng, uint32_t stage, int lane, int debug) {
+  if (!(debug & 16)) fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {   // lane 0 owns the first row of the warp's 32: its (w, h, b) are the box origin
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(mapO), "r"(stage), "r"(ng), "r"(ri.w),
@@ -407,8 +407,8 @@ __device__ __forceinline__ void flush32_tma(const CUtensorMap* mapO, const RowIn
   }
 }
 // the staging tile may be rewritten once the previous store has finished READING it
-__device__ __forceinline__ void tma_store_wait_read(int lane) {
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+__device__ __forceinline__ void tma_store_wait_read(int lane, int debug) {
+  if (lane == 0 && !(debug & 8)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
 }
 
@@ -454,9 +454,9 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUten
           }
         }
         if (p.tma_store) {
-          tma_store_wait_read(lane);
+          tma_store_wait_read(lane, p.debug);
           stage32(va, stage, lane);
-          flush32_tma(mapO, ri, ng + h, stage, lane);
+          flush32_tma(mapO, ri, ng + h, stage, lane, p.debug);
         } else {
           stage32(va, stage, lane);
           flush32(p, ri, ng + h, stage, meta, lane);
@@ -474,9 +474,9 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUten
     if (g0 + 32 < BNW) load32(g0 + 32, vb);
     epi_math32(e, ng, va);
     if (p.tma_store) {
-      tma_store_wait_read(lane);
+      tma_store_wait_read(lane, p.debug);
       stage32(va, stage, lane);
-      flush32_tma(mapO, ri, ng, stage, lane);
+      flush32_tma(mapO, ri, ng, stage, lane, p.debug);
     } else {
       stage32(va, stage, lane);
       flush32(p, ri, ng, stage, meta, lane);
@@ -486,9 +486,9 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUten
       if (g0 + 64 < BNW) load32(g0 + 64, va);
       epi_math32(e, ng + 32, vb);
       if (p.tma_store) {
-        tma_store_wait_read(lane);
+        tma_store_wait_read(lane, p.debug);
         stage32(vb, stage, lane);
-        flush32_tma(mapO, ri, ng + 32, stage, lane);
+        flush32_tma(mapO, ri, ng + 32, stage, lane, p.debug);
       } else {
         stage32(vb, stage, lane);
         flush32(p, ri, ng + 32, stage, meta, lane);
@@ -1065,8 +1065,14 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   int BN;
   if (p.Npad <= 64) BN = p.Npad;
   else if (pair) BN = (p.Npad % 256 == 0 && (long long)((ntiles + 1) / 2) * (p.Npad / 256) >= sm_count() / 2) ? 256 : 128;
-  else if (p.Npad % 256 == 0 && (long long)ntiles * (p.Npad / 256) >= sm_count()) BN = 256;   // wide tiles only if they still fill the chip
-  else BN = 128;
+  else if (p.Npad % 256 == 0) {
+    // 128 x 128 MMAs are bound by shared-memory operand reads (878 TFLOP/s issue-only on B200 vs 1398 for 128 x 256,
+    // profiles/r01_gemm_bottleneck.txt): cost of a tile ~ BN / rate(BN); pick the width with fewer (waves x tile cost)
+    const long long t128 = (long long)ntiles * (p.Npad / 128), t256 = (long long)ntiles * (p.Npad / 256);
+    const long long sms = sm_count();
+    const double c128 = (double)((t128 + sms - 1) / sms) * (128.0 / 878.0), c256 = (double)((t256 + sms - 1) / sms) * (256.0 / 1398.0);
+    BN = c256 <= c128 ? 256 : 128;
+  } else BN = 128;
   const int boxN = pair ? BN / 2 : BN;
   CUtensorMap maps[B200_MAX_SRC];
   memset(maps, 0, sizeof(maps));

@@ -238,11 +238,30 @@ __global__ void __launch_bounds__(SMP_THREADS) edm_phase_kernel(int phase, float
 
 __global__ void edm_commit_step_kernel(int* step_ctr) { step_ctr[0] = step_ctr[1]; }
 
-__global__ void finalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int unnormalize) {
+__global__ void finalize_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int flags) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = fminf(fmaxf(x[i], -1.f), 1.f);
-  out[i] = unnormalize ? __fmul_rn(__fadd_rn(v, 1.f), 0.5f) : v;
+  const float v = (flags & 2) ? x[i] : fminf(fmaxf(x[i], -1.f), 1.f);
+  out[i] = (flags & 1) ? __fmul_rn(__fadd_rn(v, 1.f), 0.5f) : v;
+}
+
+// RePaint conditioning: where the mask is set, x becomes q_sample(known) = alpha * known + sigma * noise (torch evaluates the two
+// products and the sum separately: no FMA contraction here either); elsewhere x is kept.  mask: uint8 [B, HW], shared by the C channels.
+__global__ void inpaint_mix_kernel(float* __restrict__ x, const float* __restrict__ known, const uint8_t* __restrict__ mask,
+                                   const float* __restrict__ noise, float alpha, float sigma, int C, long long hw, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long b = i / (C * hw), p = i % hw;
+  if (!mask[b * hw + p]) return;
+  const float nz = noise != nullptr ? __fmul_rn(sigma, noise[i]) : 0.f;
+  x[i] = __fadd_rn(__fmul_rn(alpha, known[i]), nz);
+}
+
+// q_sample_from_to: x = x * c1 + (noise * c2) / alpha with c1 = alpha_to / alpha, c2 = sigma_to * alpha - sigma * alpha_to
+__global__ void renoise_kernel(float* __restrict__ x, const float* __restrict__ noise, float c1, float c2, float alpha, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  x[i] = __fadd_rn(__fmul_rn(x[i], c1), __fdiv_rn(__fmul_rn(noise[i], c2), alpha));
 }
 
 int smp_smem(long long chw) { return chw <= SMP_CACHE_FLOATS ? (int)(chw * sizeof(float)) : 0; }
@@ -290,6 +309,24 @@ extern "C" int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, floa
     B200_LAUNCH_OK();
   }
   edm_phase_kernel<<<B, SMP_THREADS, smem, st>>>(phase, x, x_hat, x1, d, net_in, pred, eps, coefs, step_ctr, slots, R, B, chw, cond_scale, q);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_inpaint_mix(float* x, const float* known, const uint8_t* mask, const float* noise, float alpha, float sigma, int B, int C,
+                                int64_t hw, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && known && mask && B > 0 && C > 0 && hw > 0, "inpaint_mix: bad args");
+  const long long n = (long long)B * C * hw;
+  inpaint_mix_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, known, mask, noise, alpha, sigma, C, hw, n);
+  B200_LAUNCH_OK();
+  return B200_OK;
+}
+
+extern "C" int b200_renoise(float* x, const float* noise, float c1, float c2, float alpha, int64_t n, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(x && noise && n > 0, "renoise: bad args");
+  renoise_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, noise, c1, c2, alpha, n);
   B200_LAUNCH_OK();
   return B200_OK;
 }

@@ -87,8 +87,8 @@ class ElucidatedImagen(_SamplerBase):
                         inpaint_videos=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5, init_images=None,
                         skip_steps=None, sigma_min=None, sigma_max=None, text_embeds=None, text_mask=None, lowres_cond_img=None,
                         lowres_noise_times=None, **unsupported):
-        for name, val in dict(inpaint_videos=inpaint_videos, inpaint_images=inpaint_images, inpaint_masks=inpaint_masks,
-                              init_images=init_images, skip_steps=skip_steps, **unsupported).items():
+        inpaint_images = default(inpaint_videos, inpaint_images)
+        for name, val in unsupported.items():
             if exists(val):
                 raise NotImplementedError(f'one_unet_sample({name}=...) is outside the B200 sampling hot path')
         if not clamp:
@@ -121,8 +121,19 @@ class ElucidatedImagen(_SamplerBase):
             x, x_hat, x1, d, eps, step_ctr = (st_[n] for n in ('x', 'x_hat', 'x1', 'd', 'eps', 'step_ctr'))
             st_['coefs'][:coefs.shape[0]].copy_(coefs)
             coefs = st_['coefs']
-            step_ctr.zero_()
             x.copy_(init_sigma * torch.randn(shape, device=device))            # :442
+            if exists(init_images):
+                x.add_(init_images.to(device=device, dtype=torch.float32))     # :446-447
+            skip = default(skip_steps, 0)                                      # :476-477
+            assert 0 <= skip <= N
+            step_ctr.fill_(skip)                                               # step index (committed, staged)
+            if skip:
+                plan.slots.fill_(2 * skip)                                     # two network evaluations per skipped (non-final) step
+            has_inpainting = exists(inpaint_images) and exists(inpaint_masks)
+            if has_inpainting:                                                 # :455-462
+                known = self.resize_to(self.normalize_img(inpaint_images.to(device=device, dtype=torch.float32)), W).contiguous()
+                mask = self.resize_to(inpaint_masks.to(device)[:, None].float(), W).bool().to(torch.uint8).contiguous()
+                assert known.shape == tuple(shape) and mask.shape == (B, 1, H, W)
             net_in = plan.x_in
             lib = plan.lib
             thr = int(bool(dynamic_threshold))
@@ -148,7 +159,34 @@ class ElucidatedImagen(_SamplerBase):
                 plan.launch()
                 phase(1)
 
-            n_full = N - 1
+            out = torch.empty(shape, dtype=torch.float32, device=device)
+            if has_inpainting:
+                # RePaint (:481-536): each step is resampled at the same sigma, so the host drives the loop (eager launches) and
+                # rewrites the device-side step / slot counters before every resample
+                sig = self.sample_schedule(N, hp.rho, sigma_min, sigma_max).tolist()
+                st = torch.cuda.current_stream(device).cuda_stream
+                launches = 0
+                for i in range(skip, N):
+                    last_t = i == N - 1
+                    for r in reversed(range(inpaint_resample_times)):
+                        step_ctr.fill_(i)
+                        plan.slots.fill_(2 * i)
+                        # x_hat = x + added_noise; masked pixels must become known + added_noise (:498-499): paste `known` into x first
+                        _lib.check(lib.b200_inpaint_mix(x.data_ptr(), known.data_ptr(), mask.data_ptr(), None, 1.0, 0.0, B, Cimg, H * W, st),
+                                   'b200_inpaint_mix')
+                        (last_step if last_t else full_step)()
+                        launches += (1 if last_t else 2) * plan.n_launches + 8
+                        if not (r == 0 or last_t):                             # :533-536
+                            rn = torch.randn(shape, device=device)
+                            _lib.check(lib.b200_renoise(x.data_ptr(), rn.data_ptr(), 1.0, sig[i] - sig[i + 1], 1.0, x.numel(), st), 'b200_renoise')
+                self.last_launch_count = launches
+                _lib.check(lib.b200_finalize_images(x.data_ptr(), x.data_ptr(), x.numel(), 0, st), 'b200_finalize_images')     # clamp :538
+                _lib.check(lib.b200_inpaint_mix(x.data_ptr(), known.data_ptr(), mask.data_ptr(), None, 1.0, 0.0, B, Cimg, H * W, st),
+                           'b200_inpaint_mix')                                 # :541-542
+                _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), 2 | int(self.auto_normalize_img), st),
+                           'b200_finalize_images')
+                return out
+            n_full = max(0, N - 1 - skip)
             it = range(n_full)
             if use_tqdm:
                 try:
@@ -170,9 +208,9 @@ class ElucidatedImagen(_SamplerBase):
             else:
                 for _ in it:
                     full_step()
-            last_step()
+            if skip < N:
+                last_step()
             self.last_launch_count = n_full * (2 * plan.n_launches + 5) + plan.n_launches + 4
-            out = torch.empty(shape, dtype=torch.float32, device=device)
             _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), int(self.auto_normalize_img),
                                                 torch.cuda.current_stream(device).cuda_stream), 'b200_finalize_images')   # :540-545
         return out
@@ -190,8 +228,7 @@ class ElucidatedImagen(_SamplerBase):
             device = default(device, self.device)
             self.reset_unets_all_one_device(device=device)
             self._check_sample_args(texts, text_embeds, text_masks, dict(cond_images=cond_images, cond_video_frames=cond_video_frames,
-                                    post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos, inpaint_images=inpaint_images,
-                                    inpaint_masks=inpaint_masks, init_images=init_images, skip_steps=skip_steps, video_frames=video_frames))
+                                    post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos, video_frames=video_frames))
             if return_pil_images:
                 raise NotImplementedError('return_pil_images: convert the returned tensor yourself')
             device = next(self.parameters()).device
@@ -203,6 +240,13 @@ class ElucidatedImagen(_SamplerBase):
             num_unets = len(self.unets)
             cond_scale = cast_tuple(cond_scale, num_unets)
             sigma_min, sigma_max = cast_tuple(sigma_min, num_unets), cast_tuple(sigma_max, num_unets)
+            if exists(inpaint_images):                                         # elucidated_imagen.py:608-613
+                if self.unconditional:
+                    batch_size = inpaint_images.shape[0]
+                assert inpaint_images.shape[0] == batch_size, 'number of inpainting images must be equal to the specified batch size on sample'
+            init_images = cast_tuple(init_images, num_unets)                   # :640-643
+            init_images = [self.normalize_img(im) if exists(im) else None for im in init_images]
+            skip_steps = cast_tuple(skip_steps, num_unets)
             img = None
             if start_at_unet_number > 1:
                 assert start_at_unet_number <= num_unets, 'must start a unet that is less than the total number of unets'
@@ -210,8 +254,9 @@ class ElucidatedImagen(_SamplerBase):
                 assert exists(start_image_or_video), 'starting image or video must be supplied if only doing upscaling'
                 img = self.resize_to(start_image_or_video.to(device), self.image_sizes[start_at_unet_number - 2])
             outputs, launches = [], 0
-            for unet_number, unet, image_size, dynamic_threshold, unet_cond_scale, unet_sigma_min, unet_sigma_max in zip(
-                    range(1, num_unets + 1), self.unets, self.image_sizes, self.dynamic_thresholding, cond_scale, sigma_min, sigma_max):
+            for unet_number, unet, image_size, dynamic_threshold, unet_cond_scale, unet_sigma_min, unet_sigma_max, unet_init_images, \
+                    unet_skip_steps in zip(range(1, num_unets + 1), self.unets, self.image_sizes, self.dynamic_thresholding, cond_scale, sigma_min,
+                                           sigma_max, init_images, skip_steps):
                 if unet_number < start_at_unet_number:
                     continue
                 assert not isinstance(unet, NullUnet), 'cannot sample from null unet'
@@ -219,7 +264,12 @@ class ElucidatedImagen(_SamplerBase):
                 if unet.lowres_cond:
                     lowres_cond_img, lowres_noise_times = self._lowres_conditioning(img, image_size, batch_size, lowres_sample_noise_level, device)
                 shape = (batch_size, self.channels, image_size, image_size)
+                if exists(unet_init_images):
+                    unet_init_images = self.resize_to(unet_init_images.to(device), image_size)   # :709-710
                 img = self.one_unet_sample(unet, shape, unet_number=unet_number, text_embeds=text_embeds, text_mask=text_masks,
+                                           inpaint_images=inpaint_images, inpaint_masks=inpaint_masks,
+                                           inpaint_resample_times=inpaint_resample_times, init_images=unet_init_images,
+                                           skip_steps=unet_skip_steps,
                                            sigma_min=unet_sigma_min, sigma_max=unet_sigma_max, cond_scale=unet_cond_scale,
                                            lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
                                            dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm)

@@ -131,6 +131,16 @@ class GaussianDiffusionContinuousTimes(nn.Module):
         return coefs, log_snr
 
 
+    def repaint_coefficients(self, device):
+        """Per-step scalars of the RePaint inpainting glue, [T, 5] fp32 = (alpha_t, sigma_t) of q_sample (:272-284) and
+        (c1, c2, alpha_from) of q_sample_from_to(x, t_next -> t) (:286-306), with the reference's torch ops on `device`."""
+        times = torch.linspace(1., 0., self.num_timesteps + 1, device=device)
+        t, t_next = times[:-1], times[1:]
+        alpha, sigma = log_snr_to_alpha_sigma(self.log_snr(t))                 # "to" of the re-noising, and q_sample's time
+        alpha_f, sigma_f = log_snr_to_alpha_sigma(self.log_snr(t_next))        # "from"
+        return torch.stack((alpha, sigma, alpha / alpha_f, sigma * alpha_f - sigma_f * alpha, alpha_f), dim=1).contiguous()
+
+
 def quantile_ranks(n, q, device):
     """(lower rank, upper rank, lerp weight) exactly as torch.quantile's linear interpolation computes them."""
     rank = torch.tensor(q, dtype=torch.float32, device=device) * (n - 1)
@@ -273,8 +283,9 @@ class Imagen(_SamplerBase):
                       text_mask=None, cond_images=None, inpaint_images=None, inpaint_masks=None, init_images=None, skip_steps=None,
                       cond_scale=1, pred_objective='noise', dynamic_threshold=True, use_tqdm=True, **unsupported):
         """Imagen.p_sample_loop (:2167-2289): T ancestral steps; one CUDA-graph replay per step."""
-        for name, val in dict(cond_images=cond_images, inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, init_images=init_images,
-                              skip_steps=skip_steps, **{k: v for k, v in unsupported.items() if k != 'inpaint_resample_times'}).items():
+        inpaint_resample_times = unsupported.pop('inpaint_resample_times', 5)
+        inpaint_images = default(unsupported.pop('inpaint_videos', None), inpaint_images)
+        for name, val in dict(cond_images=cond_images, **unsupported).items():
             if exists(val):
                 raise NotImplementedError(f'p_sample_loop({name}=...) is outside the B200 sampling hot path')
         assert not (cond_scale != 1. and not self.can_classifier_guidance), \
@@ -297,6 +308,17 @@ class Imagen(_SamplerBase):
             q_lo, q_hi, q_w = quantile_ranks(chw, self.dynamic_thresholding_percentile, device)
             x = plan.x_in
             x.copy_(torch.randn(shape, device=device))                         # :2195
+            if exists(init_images):
+                x.add_(init_images.to(device=device, dtype=torch.float32))     # :2205-2206
+            skip = default(skip_steps, 0)                                      # :2230-2231
+            assert 0 <= skip <= T
+            if skip:
+                plan.slots.fill_(skip)                                         # the device-side schedule slot the first step reads
+            has_inpainting = exists(inpaint_images) and exists(inpaint_masks)
+            if has_inpainting:                                                 # :2216-2222
+                known = self.resize_to(self.normalize_img(inpaint_images.to(device=device, dtype=torch.float32)), W).contiguous()
+                mask = self.resize_to(inpaint_masks.to(device)[:, None].float(), W).bool().to(torch.uint8).contiguous()
+                assert known.shape == tuple(shape) and mask.shape == (B, 1, H, W)
             # persistent per-plan sampler buffers: the captured step graph bakes their addresses and is reused by later sample() calls
             st_ = plan.sampler_state.setdefault('ddpm', {})
             if 'noise' not in st_:
@@ -316,11 +338,38 @@ class Imagen(_SamplerBase):
                                               R, B, chw, float(cond_scale), objective, int(bool(dynamic_threshold)), q_lo, q_hi, q_w, st),
                            'b200_ddpm_step')
 
-            self.last_launch_count = self._run_steps(one_step, T, plan, device, use_tqdm, launches_per_step=plan.n_launches + 2,
-                                                     graph_cache=st_['graphs'], graph_key=key)
             out = torch.empty(shape, dtype=torch.float32, device=device)
-            _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), int(self.auto_normalize_img),
-                                                torch.cuda.current_stream(device).cuda_stream), 'b200_finalize_images')   # :2281, :2288
+            if not has_inpainting:
+                self.last_launch_count = self._run_steps(one_step, T - skip, plan, device, use_tqdm, launches_per_step=plan.n_launches + 2,
+                                                         graph_cache=st_['graphs'], graph_key=key)
+                _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), int(self.auto_normalize_img),
+                                                    torch.cuda.current_stream(device).cuda_stream), 'b200_finalize_images')   # :2281, :2288
+            else:
+                # RePaint (:2245-2279): every timestep is resampled `inpaint_resample_times` times at the SAME schedule slot, so the
+                # loop is driven from the host (eager launches; the slot is rewritten before every network evaluation)
+                rp = noise_scheduler.repaint_coefficients(device).tolist()
+                st = torch.cuda.current_stream(device).cuda_stream
+                launches = 0
+                for i in range(skip, T):
+                    a_t, s_t, c1, c2, a_from = rp[i]
+                    last_t = i == T - 1                                        # times_next == 0
+                    for r in reversed(range(inpaint_resample_times)):
+                        qn = torch.randn_like(x)                               # q_sample's randn_like (:280)
+                        _lib.check(lib.b200_inpaint_mix(x.data_ptr(), known.data_ptr(), mask.data_ptr(), qn.data_ptr(), a_t, s_t, B, Cimg,
+                                                        H * W, st), 'b200_inpaint_mix')
+                        plan.slots.fill_(i)
+                        one_step()
+                        launches += plan.n_launches + 4
+                        if not (r == 0 or last_t):                             # :2271-2278
+                            rn = torch.randn_like(x)
+                            _lib.check(lib.b200_renoise(x.data_ptr(), rn.data_ptr(), c1, c2, a_from, x.numel(), st), 'b200_renoise')
+                            launches += 2
+                self.last_launch_count = launches
+                _lib.check(lib.b200_finalize_images(x.data_ptr(), x.data_ptr(), x.numel(), 0, st), 'b200_finalize_images')     # :2281 clamp
+                _lib.check(lib.b200_inpaint_mix(x.data_ptr(), known.data_ptr(), mask.data_ptr(), None, 1.0, 0.0, B, Cimg, H * W, st),
+                           'b200_inpaint_mix')                                 # :2285-2286
+                _lib.check(lib.b200_finalize_images(x.data_ptr(), out.data_ptr(), out.numel(), 2 | int(self.auto_normalize_img), st),
+                           'b200_finalize_images')                             # :2288
         return out
 
     @staticmethod
@@ -361,15 +410,17 @@ class Imagen(_SamplerBase):
         self.eval()
         try:
             return self._sample(texts, text_masks, text_embeds, dict(video_frames=video_frames, cond_images=cond_images,
-                                cond_video_frames=cond_video_frames, post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos,
-                                inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, init_images=init_images, skip_steps=skip_steps),
+                                cond_video_frames=cond_video_frames, post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos),
                                 batch_size, cond_scale, lowres_sample_noise_level, start_at_unet_number, start_image_or_video,
-                                stop_at_unet_number, return_all_unet_outputs, return_pil_images, device, use_tqdm)
+                                stop_at_unet_number, return_all_unet_outputs, return_pil_images, device, use_tqdm,
+                                options=dict(inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times,
+                                             init_images=init_images, skip_steps=skip_steps))
         finally:
             self.train(was_training)
 
     def _sample(self, texts, text_masks, text_embeds, unsupported, batch_size, cond_scale, lowres_sample_noise_level, start_at_unet_number,
-                start_image_or_video, stop_at_unet_number, return_all_unet_outputs, return_pil_images, device, use_tqdm):
+                start_image_or_video, stop_at_unet_number, return_all_unet_outputs, return_pil_images, device, use_tqdm, options=None):
+        options = dict(options or {})
         device = default(device, self.device)
         self.reset_unets_all_one_device(device=device)
         self._check_sample_args(texts, text_embeds, text_masks, unsupported)
@@ -384,6 +435,14 @@ class Imagen(_SamplerBase):
         lowres_sample_noise_level = default(lowres_sample_noise_level, self.lowres_sample_noise_level)
         num_unets = len(self.unets)
         cond_scale = cast_tuple(cond_scale, num_unets)
+        inpaint_images, inpaint_masks = options.get('inpaint_images'), options.get('inpaint_masks')
+        if exists(inpaint_images):                                             # :2343-2350
+            if self.unconditional:
+                batch_size = inpaint_images.shape[0]
+            assert inpaint_images.shape[0] == batch_size, 'number of inpainting images must be equal to the specified batch size on sample'
+        init_images = cast_tuple(options.get('init_images'), num_unets)        # :2385-2388
+        init_images = [self.normalize_img(im) if exists(im) else None for im in init_images]
+        skip_steps = cast_tuple(options.get('skip_steps'), num_unets)
         img = None
         if start_at_unet_number > 1:                                           # :2396-2403
             assert start_at_unet_number <= num_unets, 'must start a unet that is less than the total number of unets'
@@ -391,9 +450,9 @@ class Imagen(_SamplerBase):
             assert exists(start_image_or_video), 'starting image or video must be supplied if only doing upscaling'
             img = self.resize_to(start_image_or_video.to(device), self.image_sizes[start_at_unet_number - 2])
         outputs, launches = [], 0
-        for unet_number, unet, channel, image_size, noise_scheduler, pred_objective, dynamic_threshold, unet_cond_scale in zip(
-                range(1, num_unets + 1), self.unets, self.sample_channels, self.image_sizes, self.noise_schedulers, self.pred_objectives,
-                self.dynamic_thresholding, cond_scale):
+        for unet_number, unet, channel, image_size, noise_scheduler, pred_objective, dynamic_threshold, unet_cond_scale, unet_init_images, \
+                unet_skip_steps in zip(range(1, num_unets + 1), self.unets, self.sample_channels, self.image_sizes, self.noise_schedulers,
+                                       self.pred_objectives, self.dynamic_thresholding, cond_scale, init_images, skip_steps):
             if unet_number < start_at_unet_number:
                 continue
             assert not isinstance(unet, NullUnet), 'one cannot sample from null / placeholder unets'
@@ -401,9 +460,14 @@ class Imagen(_SamplerBase):
             if unet.lowres_cond:
                 lowres_cond_img, lowres_noise_times = self._lowres_conditioning(img, image_size, batch_size, lowres_sample_noise_level, device)
             shape = (batch_size, self.channels, image_size, image_size)
+            if exists(unet_init_images):
+                unet_init_images = self.resize_to(unet_init_images.to(device), image_size)   # :2453-2454
             img = self.p_sample_loop(unet, shape, text_embeds=text_embeds, text_mask=text_masks, cond_scale=unet_cond_scale,
                                      lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times, noise_scheduler=noise_scheduler,
-                                     pred_objective=pred_objective, dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm)
+                                     pred_objective=pred_objective, dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm,
+                                     inpaint_images=inpaint_images, inpaint_masks=inpaint_masks,
+                                     inpaint_resample_times=options.get('inpaint_resample_times', 5), init_images=unet_init_images,
+                                     skip_steps=unet_skip_steps)
             launches += self.last_launch_count
             outputs.append(img)
             if exists(stop_at_unet_number) and stop_at_unet_number == unet_number:

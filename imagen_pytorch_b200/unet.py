@@ -438,6 +438,21 @@ class UnetPlan:
         """[{B,H,W,N,K,...}] of every b200_conv_gemm launch of one evaluation, in launch order (profiling aid)."""
         return [c.desc for c in self._keep if isinstance(c, ops.GemmCall)]
 
+    def launch_timed(self):
+        """Profiling aid: one evaluation with a CUDA-event pair around every C-ABI call -> [(name, microseconds)].
+        The host runs ahead of the GPU (one call = one to five kernels), so each delta is that call's execution time with the
+        caches in the state the previous call left them -- what the captured graph sees, unlike ncu's flushed-cache numbers."""
+        st = torch.cuda.current_stream(self.device)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self._ops) + 1)]
+        evs[0].record(st)
+        for i, (fn, args, name) in enumerate(self._ops):
+            rc = fn(*args, st.cuda_stream)
+            if rc != 0:
+                raise _lib.B200Error(f'{name} failed ({rc}): {self.lib.b200_last_error().decode()}')
+            evs[i + 1].record(st)
+        torch.cuda.synchronize(self.device)
+        return [(self._ops[i][2], evs[i].elapsed_time(evs[i + 1]) * 1e3) for i in range(len(self._ops))]
+
     def launch(self, stream=None):
         """Enqueue one U-Net evaluation (x_in -> pred) on the current stream. CUDA-graph capturable."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream

@@ -276,8 +276,17 @@ int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, float* d, float
                    int32_t* slots, int R, int B, int64_t chw, float cond_scale, int thresholding,
                    int32_t q_lo, int32_t q_hi, float q_w, void* stream);
 
-/* out = (clamp(x, -1, 1) + 1) * 0.5 (imagen_pytorch.py:2281,2288) or just the clamp. */
-int b200_finalize_images(const float* x, float* out, int64_t n, int unnormalize, void* stream);
+/* RePaint inpainting conditioning (imagen_pytorch.py:2248-2250, :2285-2286): where mask[b, p] != 0 (uint8 [B, HW], shared by the C
+ * channels) x <- alpha * known + sigma * noise (q_sample :272-284; noise may be NULL with sigma == 0 for the final paste). */
+int b200_inpaint_mix(float* x, const float* known, const uint8_t* mask, const float* noise, float alpha, float sigma,
+                     int B, int C, int64_t hw, void* stream);
+/* q_sample_from_to (imagen_pytorch.py:286-306), the RePaint re-noising between resamples:
+ * x <- x * c1 + (noise * c2) / alpha, c1 = alpha_to / alpha, c2 = sigma_to * alpha - sigma * alpha_to (tabulated on the host). */
+int b200_renoise(float* x, const float* noise, float c1, float c2, float alpha, int64_t n, void* stream);
+
+/* flags bit 0: out = (v + 1) * 0.5 (unnormalize_zero_to_one, imagen_pytorch.py:2288); bit 1: skip the clamp(x, -1, 1) of :2281
+ * (the caller already clamped, then pasted the inpainting pixels). */
+int b200_finalize_images(const float* x, float* out, int64_t n, int flags, void* stream);
 
 #ifdef __cplusplus
 }

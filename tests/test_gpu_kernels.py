@@ -258,6 +258,48 @@ def test_layernorm_gain_only_with_residual(Cc, residual):
     assert_close(out, ref, rtol=8e-3, atol=4e-3)
 
 
+@pytest.mark.parametrize('Cs,film,pitch', [([128], True, 0), ([64, 64], True, 32), ([256], False, 0), ([256, 128], True, 0), ([16], False, 8)])
+def test_rmsnorm_film_silu_many_rows(Cs, film, pitch):
+    """Many rows (several waves of blocks), ragged tail, strided sources."""
+    B, n = 5, 4099 * (8 if sum(Cs) <= 16 else 1)
+    M, Ct = B * n, sum(Cs)
+    wide = [rnd(M, c + pitch, seed=i).to(BF16) for i, c in enumerate(Cs)]
+    srcs = [w[:, :c] for w, c in zip(wide, Cs)]
+    gamma = rnd(Ct, seed=5).abs() + 0.5
+    fl = rnd(B, 2 * Ct + 16, scale=0.3, seed=6) if film else None
+    out = torch.zeros(M, Ct, dtype=BF16, device=DEV)
+    sa = (Src * len(srcs))(*[Src(w.data_ptr(), c, w.shape[1]) for w, c in zip(wide, Cs)])
+    g = (gamma * math.sqrt(Ct)).contiguous()
+    _lib.call('b200_rmsnorm_film_silu', sa, len(srcs), 2 ** -0.5, g.data_ptr(), fl.data_ptr() if film else None, fl.shape[1] if film else 0, n,
+              out.data_ptr(), Ct, M, stream())
+    torch.cuda.synchronize()
+    x = srcs[0].float() if len(srcs) == 1 else torch.cat((srcs[0].float(), srcs[1].float() * 2 ** -0.5), dim=1)
+    y = F.normalize(x, dim=1) * math.sqrt(Ct) * gamma
+    if film:
+        f = fl.repeat_interleave(n, dim=0)
+        y = y * (f[:, :Ct] + 1) + f[:, Ct:2 * Ct]
+    assert_close(out, F.silu(y), rtol=8e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize('Cc,residual,pitch', [(128, True, 0), (128, False, 64), (256, True, 8), (512, True, 0), (64, False, 0)])
+def test_layernorm_many_rows(Cc, residual, pitch):
+    M = 20495 * (2 if Cc >= 512 or Cc <= 64 else 1)
+    xw = rnd(M, Cc + pitch, scale=2.0).to(BF16)
+    x = xw[:, :Cc]
+    g = rnd(Cc, seed=1).abs() + 0.5
+    beta = rnd(Cc, seed=3)
+    rw = rnd(M, Cc + pitch, seed=2).to(BF16) if residual else None
+    out = torch.zeros(M, Cc, dtype=BF16, device=DEV)
+    _lib.call('b200_layernorm', xw.data_ptr(), Cc + pitch, g.data_ptr(), beta.data_ptr(), 1e-5, rw.data_ptr() if residual else None, Cc + pitch,
+              out.data_ptr(), Cc, M, Cc, stream())
+    torch.cuda.synchronize()
+    xf = x.float()
+    ref = (xf - xf.mean(-1, keepdim=True)) * (xf.var(-1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * g + beta
+    if residual:
+        ref = ref + rw[:, :Cc].float()
+    assert_close(out, ref, rtol=8e-3, atol=4e-3)
+
+
 @pytest.mark.parametrize('n,Cc', [(4096, 128), (64, 1024), (300, 40)])
 def test_global_context_gate_and_gate_residual(n, Cc):
     B = 3

@@ -11,6 +11,7 @@ import os
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 import imagen_pytorch_b200 as b2
 from imagen_pytorch_b200 import _lib
@@ -150,6 +151,84 @@ def test_elucidated_cascade_matches_oracle_with_shared_noise():
     record('edm_cascade', mean_abs=d.mean(), max_abs=d.max())
     # sigma_max = 80: the first Heun steps run the untrained net on |x| ~ 80 inputs, which amplifies bf16 noise (measured mean 1.1e-2)
     assert d.mean() < 3e-2
+
+
+def _cascade_pair(g):
+    ub = make_unet(g['base_kwargs'], 'test_base', g['wseed_base'])
+    us = make_unet(g['sr_kwargs'], 'test_sr', g['wseed_sr'], lowres_cond=True)
+    models = [(synth_weights('test_base', g['wseed_base']), unet_ref.unet_config(**g['base_kwargs'])),
+              (synth_weights('test_sr', g['wseed_sr']), unet_ref.unet_config(**g['sr_kwargs'], lowres_cond=True))]
+    return ub, us, models
+
+
+def _known_pixels(g):
+    m = g['inpaint_masks'][:, None].expand(-1, 3, -1, -1)
+    return m, ((g['inpaint_images'] * 2 - 1 + 1) * 0.5)[m]
+
+
+def test_ddpm_sampler_options_match_oracle_with_shared_noise():
+    """SURVEY.md 8f.2 on the DDPM loop: init_images + skip_steps (graph replays from a later schedule slot) and RePaint inpainting
+    (host-driven resampling, b200_inpaint_mix / b200_renoise) against the oracle on the same noise draws."""
+    g = load_golden('ddpm_options_dim32.pt')
+    ub, us, models = _cascade_pair(g)
+    im = b2.Imagen((ub, us), image_sizes=(16, 32), timesteps=g['timesteps'], text_embed_dim=64).to(DEV)
+    te = g['text_embeds']
+    common = dict(cond_scale=g['cond_scale'], return_all_unet_outputs=True)
+    torch.manual_seed(31)
+    o_init = im.sample(text_embeds=te.to(DEV), use_tqdm=False, init_images=g['init_images'].to(DEV), skip_steps=g['skip_steps'], **common)
+    torch.manual_seed(31)
+    with torch.no_grad():
+        r_init = sampler_ref.imagen_sample(models, (16, 32), text_embeds=te, timesteps=g['timesteps'], init_images=g['init_images'],
+                                           skip_steps=g['skip_steps'], randn=cuda_randn, **common)
+    torch.manual_seed(37)
+    o_inp = im.sample(text_embeds=te.to(DEV), use_tqdm=False, inpaint_images=g['inpaint_images'].to(DEV), inpaint_masks=g['inpaint_masks'].to(DEV),
+                      inpaint_resample_times=g['inpaint_resample_times'], **common)
+    torch.manual_seed(37)
+    with torch.no_grad():
+        r_inp = sampler_ref.imagen_sample(models, (16, 32), text_embeds=te, timesteps=g['timesteps'], inpaint_images=g['inpaint_images'],
+                                          inpaint_masks=g['inpaint_masks'], inpaint_resample_times=g['inpaint_resample_times'],
+                                          randn=cuda_randn, **common)
+    d = [(a.cpu() - b).abs().mean().item() for a, b in zip(o_init + o_inp, r_init + r_inp)]
+    record('ddpm_options', init_base=d[0], init_sr=d[1], inpaint_base=d[2], inpaint_sr=d[3])
+    assert max(d) < 1e-2
+    m, known = _known_pixels(g)
+    assert torch.equal(o_inp[1].cpu()[m], known)            # the final paste is exact (imagen_pytorch.py:2285-2288)
+    # skipping every step returns the clamped start image: randn + init, nothing else
+    torch.manual_seed(41)
+    o_skip = im.sample(text_embeds=te.to(DEV), use_tqdm=False, init_images=g['init_images'].to(DEV), skip_steps=g['timesteps'],
+                       stop_at_unet_number=1, **common)[0]
+    torch.manual_seed(41)
+    start = torch.randn(2, 3, 16, 16, device=DEV) + F.interpolate(g['init_images'].to(DEV) * 2 - 1, 16, mode='nearest')
+    assert torch.equal(o_skip, (start.clamp(-1, 1) + 1) * 0.5)
+
+
+def test_elucidated_sampler_options_match_oracle_with_shared_noise():
+    g = load_golden('edm_options_dim32.pt')
+    ub, us, models = _cascade_pair(g)
+    el = b2.ElucidatedImagen((ub, us), image_sizes=(16, 32), text_embed_dim=64, num_sample_steps=g['num_sample_steps'],
+                             sigma_max=g['sigma_max']).to(DEV)
+    te = g['text_embeds']
+    hp = dict(num_sample_steps=g['num_sample_steps'], sigma_max=g['sigma_max'])
+    common = dict(cond_scale=g['cond_scale'], return_all_unet_outputs=True)
+    torch.manual_seed(43)
+    o_init = el.sample(text_embeds=te.to(DEV), use_tqdm=False, init_images=g['init_images'].to(DEV), skip_steps=g['skip_steps'], **common)
+    torch.manual_seed(43)
+    with torch.no_grad():
+        r_init = sampler_ref.elucidated_sample(models, (16, 32), text_embeds=te, hparams=hp, init_images=g['init_images'],
+                                               skip_steps=g['skip_steps'], randn=cuda_randn, **common)
+    torch.manual_seed(47)
+    o_inp = el.sample(text_embeds=te.to(DEV), use_tqdm=False, inpaint_images=g['inpaint_images'].to(DEV), inpaint_masks=g['inpaint_masks'].to(DEV),
+                      inpaint_resample_times=g['inpaint_resample_times'], **common)
+    torch.manual_seed(47)
+    with torch.no_grad():
+        r_inp = sampler_ref.elucidated_sample(models, (16, 32), text_embeds=te, hparams=hp, inpaint_images=g['inpaint_images'],
+                                              inpaint_masks=g['inpaint_masks'], inpaint_resample_times=g['inpaint_resample_times'],
+                                              randn=cuda_randn, **common)
+    d = [(a.cpu() - b).abs().mean().item() for a, b in zip(o_init + o_inp, r_init + r_inp)]
+    record('edm_options', init_base=d[0], init_sr=d[1], inpaint_base=d[2], inpaint_sr=d[3])
+    assert max(d) < 3e-2
+    m, known = _known_pixels(g)
+    assert torch.equal(o_inp[1].cpu()[m], known)
 
 
 def test_cuda_graph_replay_equals_eager_loop_bit_for_bit(monkeypatch):

@@ -72,6 +72,49 @@ def test_edm_cascade_matches_reference_golden():
     assert (out - g['out']).abs().max() < 2e-3
 
 
+def _cascade_models(g):
+    sdb, sds = synth_weights('test_base', g['wseed_base']), synth_weights('test_sr', g['wseed_sr'])
+    return [(sdb, unet_ref.unet_config(**g['base_kwargs'])), (sds, unet_ref.unet_config(**g['sr_kwargs'], lowres_cond=True))]
+
+
+def test_ddpm_sampler_options_match_reference_golden():
+    """init_images + skip_steps and RePaint inpainting on the DDPM cascade (imagen_pytorch.py:2205-2279), SURVEY.md 8f.2."""
+    g = load_golden('ddpm_options_dim32.pt')
+    models = _cascade_models(g)
+    common = dict(text_embeds=g['text_embeds'], timesteps=g['timesteps'], cond_scale=g['cond_scale'], return_all_unet_outputs=True)
+    with torch.no_grad():
+        torch.manual_seed(g['seed_init'])
+        a = sampler_ref.imagen_sample(models, (16, 32), init_images=g['init_images'], skip_steps=g['skip_steps'], **common)
+        torch.manual_seed(g['seed_inpaint'])
+        b = sampler_ref.imagen_sample(models, (16, 32), inpaint_images=g['inpaint_images'], inpaint_masks=g['inpaint_masks'],
+                                      inpaint_resample_times=g['inpaint_resample_times'], **common)
+    for o, r in zip(a + b, g['outs_init'] + g['outs_inpaint']):
+        assert (o - r).abs().max() < 1e-4
+    # masked pixels of the final image are the known image, bit for bit (:2285-2288)
+    m = g['inpaint_masks'][:, None].expand(-1, 3, -1, -1)
+    assert torch.equal(b[1][m], ((g['inpaint_images'] * 2 - 1 + 1) * 0.5)[m])
+
+
+def test_edm_sampler_options_match_reference_golden():
+    """The same options on ElucidatedImagen.one_unet_sample (elucidated_imagen.py:446-447, :455-462, :476-477, :498-499, :533-542)."""
+    g = load_golden('edm_options_dim32.pt')
+    models = _cascade_models(g)
+    common = dict(text_embeds=g['text_embeds'], cond_scale=g['cond_scale'], return_all_unet_outputs=True,
+                  hparams=dict(num_sample_steps=g['num_sample_steps'], sigma_max=g['sigma_max']))
+    with torch.no_grad():
+        torch.manual_seed(g['seed_init'])
+        a = sampler_ref.elucidated_sample(models, (16, 32), init_images=g['init_images'], skip_steps=g['skip_steps'], **common)
+        torch.manual_seed(g['seed_inpaint'])
+        b = sampler_ref.elucidated_sample(models, (16, 32), inpaint_images=g['inpaint_images'], inpaint_masks=g['inpaint_masks'],
+                                          inpaint_resample_times=g['inpaint_resample_times'], **common)
+    for o, r in zip(a, g['outs_init']):
+        assert (o - r).abs().max() < 1e-4
+    for o, r in zip(b, g['outs_inpaint']):
+        assert (o - r).abs().max() < 5e-3      # the SR stage amplifies fp32 re-association noise (see make_golden.py)
+    m = g['inpaint_masks'][:, None].expand(-1, 3, -1, -1)
+    assert torch.equal(b[1][m], ((g['inpaint_images'] * 2 - 1 + 1) * 0.5)[m])
+
+
 def test_schedule_known_answers():
     g = load_golden('schedules.pt')
     assert torch.allclose(sampler_ref.alpha_cosine_log_snr(g['t']), g['cosine'], atol=1e-6)

@@ -74,6 +74,6 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'child':
         child()
     else:
-        for tma, dbg in (('1', '0'), ('1', '6'), ('0', '0')):
+        for tma, dbg in (('1', '0'), ('1', '8'), ('1', '24'), ('1', '14'), ('1', '30')):
             env = dict(os.environ, B200_IMAGEN_GEMM_TMA_STORE=tma, B200_IMAGEN_GEMM_DEBUG=dbg)
             subprocess.run([sys.executable, __file__, 'child'], env=env, check=False)

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+OUT=gpurun_out
+PYT="python -m pytest -q --tb=short -p no:cacheprovider"
+timeout 900 $PYT tests/test_gpu_kernels.py -m gpu > $OUT/k_all.log 2>&1; echo "k_all $? $(tail -n1 $OUT/k_all.log)"; grep -E "^E |^FAILED" $OUT/k_all.log | head -20
+B200_IMAGEN_ROW_VPT=2 timeout 300 python tools/row_bench.py child > $OUT/row_bench2.log 2>&1; cat $OUT/row_bench2.log
+timeout 1500 $PYT tests/test_gpu_unet.py -m gpu > $OUT/u_tc.log 2>&1; echo "u_tc $? $(tail -n1 $OUT/u_tc.log)"; grep -E "^E |^FAILED" $OUT/u_tc.log | head
+timeout 600 python bench.py --steps 3 --warmup 3 --timesteps 100 --no-cpu-baseline > $OUT/bench_100.log 2>&1; echo "bench100 $?"; grep '^{' $OUT/bench_100.log | cut -c1-200
+B200_IMAGEN_ROW_STREAM=0 timeout 600 python bench.py --steps 3 --warmup 3 --timesteps 100 --no-cpu-baseline > $OUT/bench_100_nostream.log 2>&1; echo "bench100 nostream $?"; grep '^{' $OUT/bench_100_nostream.log | cut -c1-200
