@@ -41,6 +41,16 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][64] bf16 tile with XOR swizzle
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+static inline int sm_count_attn() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 struct AttnParams {
   const __nv_bfloat16* q;
   __nv_bfloat16* o;
@@ -218,6 +228,154 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attn_kernel(AttnParams p
   }
 }
 
+
+// ---- few-keys variant (cross-attention over the 39 context rows: n_keys <= 64, one K/V tile) ---------------------------------
+// The generic kernel above spends one short-lived CTA per 128 query rows (load -> compute -> 4-byte scattered stores): 126 us for
+// the 268 MB of q + o at the 64x64 level.  Here a CTA keeps K/V of its (sample, head) in shared memory, walks a contiguous range
+// of query tiles with a 3-deep cp.async ring (prefetch distance 2), needs no online rescaling (single tile), and stages O through
+// the query buffer so every store instruction writes whole 128-byte rows.
+constexpr int XA_QBUF = 3;
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) cross_attn_fewkeys_kernel(AttnParams p, int tiles_per_cta) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  uint8_t* sK = att_smem;                        // 64 x 128 B
+  uint8_t* sV = sK + ATT_BN * 128;               // 64 x 128 B
+  uint8_t* sQ = sV + ATT_BN * 128;               // XA_QBUF x 128 x 128 B
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* qb = p.q + (long long)b * p.q_bs + (long long)h * p.q_hs;
+  __nv_bfloat16* ob = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs;
+  const __nv_bfloat16* kb = p.k + (long long)b * p.kv_bs + (long long)h * p.kv_hs;
+  const __nv_bfloat16* vb = p.v + (long long)b * p.kv_bs + (long long)h * p.kv_hs;
+  const int ntiles = (p.rows + ATT_BM - 1) / ATT_BM;
+  const int t0 = blockIdx.x * tiles_per_cta;
+  const int t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+  if (t0 >= t1) return;
+
+  auto load_q = [&](int tile, int buf) {
+    uint8_t* dst = sQ + buf * ATT_BM * 128;
+    const int row0 = tile * ATT_BM;
+#pragma unroll
+    for (int i = 0; i < (ATT_BM * 8) / ATT_THREADS; ++i) {
+      const int idx = tid + i * ATT_THREADS;
+      const int r = idx >> 3, c = idx & 7;
+      if (row0 + r < p.rows) cp_async16(dst + swz(r, c), qb + (long long)(row0 + r) * p.q_rs + c * 8);
+      else *reinterpret_cast<uint4*>(dst + swz(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  load_kv_tile(sK, sV, kb, vb, 0, p.n_keys, p.kv_rs, tid);
+  load_q(t0, 0);
+  cp_async_commit();
+  if (t0 + 1 < t1) load_q(t0 + 1, 1);
+  cp_async_commit();
+
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t kbase = smem_u32(sK), vbase = smem_u32(sV);
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) % XA_QBUF;
+    cp_async_wait<1>();          // tile t (and K/V) landed; tile t+1 may still be in flight
+    __syncthreads();             // ... for every thread; also: everyone is done with the buffer refilled below
+    if (t + 2 < t1) load_q(t + 2, (t - t0 + 2) % XA_QBUF);
+    cp_async_commit();
+
+    uint8_t* sQb = sQ + buf * ATT_BM * 128;
+    const uint32_t qbase = smem_u32(sQb);
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int c = 2 * ks + (lane >> 4);
+      ldsm_x4(qbase + swz(r, c), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t b0, b1, b2, b3;
+        const int r = 8 * (2 * jp + (lane >> 4)) + (lane & 7);
+        const int c = 2 * ks + ((lane >> 3) & 1);
+        ldsm_x4(kbase + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * jp], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+        mma_bf16_16816(s[2 * jp + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+      }
+    }
+    if (p.n_keys < ATT_BN) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kidx = 8 * j + 2 * tq;
+        if (kidx >= p.n_keys) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (kidx + 1 >= p.n_keys) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx[0] = fmaxf(mx[0], fmaxf(s[j][0], s[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[j][2], s[j][3]));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+      mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+    }
+    float l[2] = {0.f, 0.f};
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(s[j][0] - mx[0]), p1 = exp2f(s[j][1] - mx[0]);
+      const float p2 = exp2f(s[j][2] - mx[1]), p3 = exp2f(s[j][3] - mx[1]);
+      l[0] += p0 + p1;
+      l[1] += p2 + p3;
+      const int kk = j >> 1;
+      if ((j & 1) == 0) { pf[kk][0] = pack_bf16x2(p0, p1); pf[kk][1] = pack_bf16x2(p2, p3); }
+      else              { pf[kk][2] = pack_bf16x2(p0, p1); pf[kk][3] = pack_bf16x2(p2, p3); }
+    }
+    float o_acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t b0, b1, b2, b3;
+        const int r = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = 2 * jp + (lane >> 4);
+        ldsm_x4_trans(vbase + swz(r, c), b0, b1, b2, b3);
+        mma_bf16_16816(o_acc[2 * jp], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b0, b1);
+        mma_bf16_16816(o_acc[2 * jp + 1], pf[kk][0], pf[kk][1], pf[kk][2], pf[kk][3], b2, b3);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+      l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+    }
+    const float inv0 = 1.f / l[0], inv1 = 1.f / l[1];
+    // ---- O -> this warp's 16 rows of the query buffer (only this warp ever read them) -> coalesced 16-byte stores
+    __syncwarp();
+    const int rl = warp * 16 + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(sQb + swz(rl, j) + 4 * tq) = pack_bf16x2(o_acc[j][0] * inv0, o_acc[j][1] * inv0);
+      *reinterpret_cast<uint32_t*>(sQb + swz(rl + 8, j) + 4 * tq) = pack_bf16x2(o_acc[j][2] * inv1, o_acc[j][3] * inv1);
+    }
+    __syncwarp();
+    const int row0 = t * ATT_BM;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = warp * 16 + it * 4 + (lane >> 3), c = lane & 7;
+      if (row0 + r < p.rows)
+        *reinterpret_cast<uint4*>(ob + (long long)(row0 + r) * p.q_rs + c * 8) = *reinterpret_cast<const uint4*>(sQb + swz(r, c));
+    }
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace
 
 int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
@@ -245,6 +403,28 @@ extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs
   p.v = reinterpret_cast<const __nv_bfloat16*>(v);
   p.q_bs = q_bs; p.q_hs = q_hs; p.kv_bs = kv_bs; p.kv_hs = kv_hs;
   p.q_rs = q_rs; p.kv_rs = kv_rs; p.rows = rows; p.n_keys = n_keys;
+  if (n_keys <= ATT_BN) {
+    static const bool on = [] { const char* e = getenv("B200_IMAGEN_XATTN_FEWKEYS"); return e == nullptr || atoi(e) != 0; }();
+    if (on) {
+      constexpr int xsmem = 2 * ATT_BN * 128 + XA_QBUF * ATT_BM * 128;
+      static bool xconfigured = false;
+      if (!xconfigured) {
+        B200_CUDA_OK(cudaFuncSetAttribute(cross_attn_fewkeys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xsmem));
+        xconfigured = true;
+      }
+      // contiguous tile ranges per CTA; one wave of CTAs (2 resident per SM) when the problem allows
+      const int ntiles = (rows + ATT_BM - 1) / ATT_BM;
+      const long long pairs = (long long)B * n_heads;
+      int splits = (int)(2ll * sm_count_attn() / pairs);
+      if (splits < 1) splits = 1;
+      if (splits > ntiles) splits = ntiles;
+      const int tiles_per_cta = (ntiles + splits - 1) / splits;
+      dim3 xgrid((ntiles + tiles_per_cta - 1) / tiles_per_cta, n_heads, B);
+      cross_attn_fewkeys_kernel<<<xgrid, ATT_THREADS, xsmem, st>>>(p, tiles_per_cta);
+      B200_LAUNCH_OK();
+      return B200_OK;
+    }
+  }
   constexpr int smem = ATT_BM * 128 + 4 * ATT_BN * 128;
   static bool configured = false;
   if (!configured) {

@@ -355,6 +355,8 @@ __global__ void gate_residual_kernel(const __nv_bfloat16* __restrict__ x, int ld
 
 // ---------------------------------------------------------------- layout gathers
 
+constexpr int IM2COL_ROWS = 32;
+
 __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restrict__ img0, int C0, const float* __restrict__ img1, int C1, int B, int H,
                                                           int W, int ks, __nv_bfloat16* __restrict__ out, int Kpad) {
   // k -> (dy, dx, channel) decode table, built once per block instead of a div/mod chain per element
@@ -371,29 +373,32 @@ __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restric
   __syncthreads();
   const int vecs = Kpad >> 3;
   const long long M = (long long)B * H * W;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * vecs) return;
-  // consecutive threads = consecutive 16-byte vectors of one patch row: the 92 MB of writes are fully coalesced
-  // (the reads gather from a < 1 MB image that lives in L1/L2)
-  const int kv = (int)(idx % vecs);
-  const long long row = idx / vecs;
-  const int k0 = kv << 3;
-  const int w = (int)(row % W), h = (int)((row / W) % H), b = (int)(row / ((long long)W * H));
-  float f[8];
+  // IM2COL_ROWS patch rows per block, so the table above is built once per IM2COL_ROWS * Kpad outputs (it used to be rebuilt for
+  // every 256 vectors = 2.9 rows, which cost more than the gather).  Consecutive threads = consecutive 16-byte vectors of a patch
+  // row: the 92 MB of writes are fully coalesced; the reads gather from a < 1 MB image that lives in L1/L2.
+  const long long row_begin = (long long)blockIdx.x * IM2COL_ROWS;
+  const int nvec = (int)((M - row_begin < IM2COL_ROWS ? M - row_begin : IM2COL_ROWS) * vecs);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int kv = i % vecs;
+    const long long row = row_begin + i / vecs;
+    const int k0 = kv << 3;
+    const int w = (int)(row % W), h = (int)((row / W) % H), b = (int)(row / ((long long)W * H));
+    float f[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int e = lut[k0 + j];
-    float v = 0.f;
-    if (e >= 0) {
-      const int hh = h + ((e >> 16) & 255) - 64, ww = w + ((e >> 8) & 255) - 64, c = e & 255;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        v = c < C0 ? __ldg(img0 + (((long long)b * C0 + c) * H + hh) * W + ww)
-                   : __ldg(img1 + (((long long)b * C1 + (c - C0)) * H + hh) * W + ww);
+    for (int j = 0; j < 8; ++j) {
+      const int e = lut[k0 + j];
+      float v = 0.f;
+      if (e >= 0) {
+        const int hh = h + ((e >> 16) & 255) - 64, ww = w + ((e >> 8) & 255) - 64, c = e & 255;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          v = c < C0 ? __ldg(img0 + (((long long)b * C0 + c) * H + hh) * W + ww)
+                     : __ldg(img1 + (((long long)b * C1 + (c - C0)) * H + hh) * W + ww);
+        }
       }
+      f[j] = v;
     }
-    f[j] = v;
+    *reinterpret_cast<uint4*>(out + row * Kpad + k0) = pack8(f);
   }
-  *reinterpret_cast<uint4*>(out + row * Kpad + k0) = pack8(f);
 }
 
 __global__ void pixel_unshuffle_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W, int C,
@@ -564,9 +569,8 @@ extern "C" int b200_im2col_init(const float* img0, int C0, const float* img1, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1), "im2col: null pointer");
   B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
-  const long long tot = (long long)B * H * W * (Kpad >> 3);
   B200_REQUIRE(Kpad * 4 <= 48 * 1024 && C0 + C1 < 256, "im2col: patch too large");
-  im2col_init_kernel<<<(unsigned)ceil_div64(tot, 256), 256, Kpad * sizeof(int), st>>>(img0, C0, img1, C1, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
+  im2col_init_kernel<<<(unsigned)ceil_div64((long long)B * H * W, IM2COL_ROWS), 256, Kpad * sizeof(int), st>>>(img0, C0, img1, C1, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
   B200_LAUNCH_OK();
   return B200_OK;
 }

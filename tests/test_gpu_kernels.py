@@ -201,7 +201,7 @@ def test_multi_query_attention(rows, nkeys, path):
 
 
 @pytest.mark.parametrize('path', ['tc', 'mma'])
-@pytest.mark.parametrize('n,nk', [(100, 39), (4096, 39), (64, 259)])
+@pytest.mark.parametrize('n,nk', [(100, 39), (4096, 39), (64, 259), (1000, 64), (300, 5), (20000, 39)])
 def test_cross_attention_layout_per_head_kv(n, nk, path):
     B, heads = 2, 8
     inner = heads * 64

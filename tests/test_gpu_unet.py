@@ -321,6 +321,23 @@ def test_cfg4_cascade_64_to_256_srunet256_smoke():
     assert torch.equal(a, b) and a.shape == (2, 3, 256, 256)
 
 
+def test_srunet1024_stage_upscale_only_smoke():
+    """the conv-only SRUnet1024 stage (imagen_pytorch.py:1771-1783) at 1024 x 1024 through the upscale-only entry
+    (start_at_unet_number / start_image_or_video, :2396-2403): 1 Mi pixel rows per sample, 8192 GEMM row tiles per conv."""
+    torch.manual_seed(0)
+    first = b2.Unet(dim=32, dim_mults=(1, 2))                       # placeholder stage 1, never planned or run
+    sr = _rand_final_conv(b2.SRUnet1024(lowres_cond=True))
+    im = b2.Imagen((first, sr), image_sizes=(256, 1024), timesteps=2).to(DEV)
+    te = torch.randn(1, 256, 768, device=DEV)
+    low = torch.rand(1, 3, 256, 256, device=DEV)
+    torch.manual_seed(4)
+    a = im.sample(text_embeds=te, cond_scale=1., use_tqdm=False, start_at_unet_number=2, start_image_or_video=low)
+    torch.manual_seed(4)
+    b = im.sample(text_embeds=te, cond_scale=1., use_tqdm=False, start_at_unet_number=2, start_image_or_video=low)
+    assert a.shape == (1, 3, 1024, 1024) and torch.isfinite(a).all() and 0 <= a.min() and a.max() <= 1 and a.std() > 1e-3
+    assert torch.equal(a, b)
+
+
 def test_cfg5_dim192_forward_properties():
     """BASELINE.json configs[4] architecture: base Unet(dim=192) (channels up to 2304 in the concat norms)."""
     torch.manual_seed(0)
