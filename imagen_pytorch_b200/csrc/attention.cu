@@ -15,7 +15,6 @@ namespace {
 
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 64;
-constexpr int ATT_D = 64;
 constexpr int ATT_THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {

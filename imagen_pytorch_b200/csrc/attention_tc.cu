@@ -28,7 +28,6 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_MAX_SM_WARPS = 16;
 constexpr int FA_DEFAULT_VARIANT = 12;   // ping-pong with 16 softmax warps (profiles/r01_attention_variant_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
@@ -313,7 +312,6 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 // warps: 0 TMA, 1 issuer A (+TMEM alloc), 2 issuer B, 3 idle, 4-7 softmax A, 8-11 softmax B.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PP_THREADS = 384;
 constexpr int PP_STAGES = 4;                       // deep K/V ring: the two groups may drift apart by more than a tile
 constexpr int PP_PH_BYTES = FA_BM * 64 * 2;        // one 64-key half of a P tile (16 KB), its own full/empty barriers
 constexpr int PP_SMEM = 2 * FA_Q_BYTES + PP_STAGES * FA_KV_BYTES + 4 * PP_PH_BYTES + 1024 + 256;   // 230656 B of the 232448 B limit
@@ -473,7 +471,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
               float p0 = ex2_approx(__uint_as_float(sr[8 * t + i]) - C);
-              float p1 = (POLY > 0 && ((8 * t + i + 1) % POLY) == POLY - 1) ? ex2_poly(__uint_as_float(sr[8 * t + i + 1]) - C)
+              float p1 = (POLY > 0 && ((8 * t + i + 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly(__uint_as_float(sr[8 * t + i + 1]) - C)
                                                                            : ex2_approx(__uint_as_float(sr[8 * t + i + 1]) - C);
               if (ragged) {
                 if (key0 + hf * 64 + c0 + 8 * t + i >= p.n_keys) p0 = 0.f;

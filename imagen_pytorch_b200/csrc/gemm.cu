@@ -21,7 +21,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_MAX_THREADS = 64 + 256;   // TMA warp + MMA warp + up to 8 epilogue warps
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int EPI_STAGE_BYTES = 2048 + 512;   // per epilogue warp: 32 rows x 64 B staging tile + 32 x 16 B row metadata
 
@@ -355,11 +354,11 @@ __device__ __forceinline__ void flush32(const GemmParams& p, const RowInfo& ri, 
   const uint32_t rd = stage + (uint32_t)rs * 64u + (uint32_t)((ch ^ ((rs >> 1) & 3)) << 4);   // + 512 per 8 rows; (row >> 1) & 3 == (rs >> 1) & 3
   __syncwarp();
   uint4 u[4];
-  uint32_t m0[4], m1[4], m2[4], m3[4];
+  uint32_t m0[4], m1[4], m2[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     u[r] = ld_shared_v4(rd + (uint32_t)r * 512u);
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(m0[r]), "=r"(m1[r]), "=r"(m2[r]), "=r"(m3[r]) : "r"(meta + (uint32_t)(8 * r + rs) * 16u) : "memory");
+    asm volatile("{\n\t.reg .b32 pad;\n\tld.shared.v4.b32 {%0, %1, %2, pad}, [%3];\n\t}" : "=r"(m0[r]), "=r"(m1[r]), "=r"(m2[r]) : "r"(meta + (uint32_t)(8 * r + rs) * 16u) : "memory");
   }
   if (col < p.N) {
     if (e.residual != nullptr) {
