@@ -67,6 +67,7 @@ SIGNATURES = {
     'b200_gca_nchunk': [_I],
     'b200_gate_residual': [_P, _I, _P, _P, _I, _P, _I, _L, _I, _I, _P],
     'b200_im2col_init': [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    'b200_im2col_init3': [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     'b200_pixel_unshuffle': [_P, _I, _I, _I, _I, _I, _P, _P],
     'b200_nchw_to_rows': [_P, _I, _I, _I, _I, _P, _I, _P],
     'b200_make_time_cond': [_P, _P, _P, _I, _I, _P, _P],
@@ -78,6 +79,8 @@ SIGNATURES = {
     'b200_headnorm_store': [_P, _I, _I, _I, _I, _P, _P, _I, _L, _L, _L, _L, _P],
     'b200_ddpm_step': [_P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _I, _F, _P],
     'b200_edm_phase': [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _F, _P],
+    'b200_ddpm_step_sc': [_P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _I, _F, _P, _P],
+    'b200_edm_phase_sc': [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _F, _I, _I, _I, _F, _P, _P],
     'b200_inpaint_mix': [_P, _P, _P, _P, _F, _F, _I, _I, _L, _P],
     'b200_renoise': [_P, _P, _F, _F, _F, _L, _P],
     'b200_finalize_images': [_P, _P, _L, _I, _P],

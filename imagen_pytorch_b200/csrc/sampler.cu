@@ -121,7 +121,7 @@ __device__ __forceinline__ float cfg_combine(const float* pred, long long idx_c,
 __global__ void __launch_bounds__(SMP_THREADS) ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ pred,
                                                                 const float* __restrict__ noise, const b200_ddpm_coef* __restrict__ coefs,
                                                                 int* __restrict__ slots, int R, int B, long long chw, float cond_scale,
-                                                                int objective, Quant q) {
+                                                                int objective, Quant q, float* __restrict__ x_start_out) {
   extern __shared__ float smp_cache[];
   __shared__ unsigned sh_hist[256 + 40];
   const int b = blockIdx.x;
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(SMP_THREADS) ddpm_step_kernel(float* __restric
   const float one_minus_c = __fsub_rn(1.f, cf.c);
   for (long long i = threadIdx.x; i < chw; i += blockDim.x) {
     const float x0 = clamp_div(cached ? smp_cache[i] : x0_of(i), s, q.dynamic);
+    if (x_start_out != nullptr) x_start_out[oc + i] = x0;      // the next step's self-conditioning input (imagen_pytorch.py:2252)
     const float xt = xb[i];
     // alpha_next * (x_t * (1 - c) / alpha + c * x_start)
     const float mean = __fmul_rn(cf.alpha_next, __fadd_rn(__fdiv_rn(__fmul_rn(xt, one_minus_c), cf.alpha), __fmul_rn(cf.c, x0)));
@@ -167,7 +168,8 @@ __global__ void __launch_bounds__(SMP_THREADS) edm_phase_kernel(int phase, float
                                                                 float* __restrict__ x1, float* __restrict__ d, float* __restrict__ net_in,
                                                                 const float* __restrict__ pred, const float* __restrict__ eps,
                                                                 const b200_edm_coef* __restrict__ coefs, int* __restrict__ step_ctr,
-                                                                int* __restrict__ slots, int R, int B, long long chw, float cond_scale, Quant q) {
+                                                                int* __restrict__ slots, int R, int B, long long chw, float cond_scale, Quant q,
+                                                                float* __restrict__ denoised_out) {
   extern __shared__ float smp_cache[];
   __shared__ unsigned sh_hist[256 + 40];
   const int b = blockIdx.x;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(SMP_THREADS) edm_phase_kernel(int phase, float
   if (phase == 1) {
     for (long long i = threadIdx.x; i < chw; i += blockDim.x) {
       const float D = clamp_div(cached ? smp_cache[i] : den_of(i), s, q.dynamic);
+      if (denoised_out != nullptr) denoised_out[oc + i] = D;   // self-conditioning input of the next evaluation (elucidated_imagen.py:518, :538)
       const float xh = x_hat[oc + i];
       const float dd = __fdiv_rn(__fsub_rn(xh, D), cf.sigma_hat);
       const float xn = __fadd_rn(xh, __fmul_rn(dt, dd));
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(SMP_THREADS) edm_phase_kernel(int phase, float
     const float half_dt = cf.half_dt;
     for (long long i = threadIdx.x; i < chw; i += blockDim.x) {
       const float D = clamp_div(cached ? smp_cache[i] : den_of(i), s, q.dynamic);
+      if (denoised_out != nullptr) denoised_out[oc + i] = D;
       const float xn1 = x1[oc + i];
       const float dp = __fdiv_rn(__fsub_rn(xn1, D), cf.sigma_next);
       x[oc + i] = __fadd_rn(x_hat[oc + i], __fmul_rn(half_dt, __fadd_rn(d[oc + i], dp)));
@@ -268,9 +272,9 @@ int smp_smem(long long chw) { return chw <= SMP_CACHE_FLOATS ? (int)(chw * sizeo
 
 }  // namespace
 
-extern "C" int b200_ddpm_step(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs, int32_t* slots, int R, int B,
-                              int64_t chw, float cond_scale, int objective, int thresholding, int32_t q_lo, int32_t q_hi, float q_w,
-                              void* stream) {
+extern "C" int b200_ddpm_step_sc(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs, int32_t* slots, int R, int B,
+                                 int64_t chw, float cond_scale, int objective, int thresholding, int32_t q_lo, int32_t q_hi, float q_w,
+                                 float* x_start_out, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(x && pred && noise && coefs && slots, "ddpm_step: null pointer");
   B200_REQUIRE(B > 0 && (R == B || R == 2 * B) && chw > 0, "ddpm_step: bad R=%d B=%d", R, B);
@@ -283,14 +287,20 @@ extern "C" int b200_ddpm_step(float* x, const float* pred, const float* noise, c
     B200_CUDA_OK(cudaFuncSetAttribute(ddpm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_CACHE_FLOATS * 4));
     cfg = true;
   }
-  ddpm_step_kernel<<<B, SMP_THREADS, smem, st>>>(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q);
+  ddpm_step_kernel<<<B, SMP_THREADS, smem, st>>>(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q, x_start_out);
   B200_LAUNCH_OK();
   return B200_OK;
 }
 
-extern "C" int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, float* d, float* net_in, const float* pred, const float* eps,
-                              const b200_edm_coef* coefs, int32_t* step_ctr, int32_t* slots, int R, int B, int64_t chw, float cond_scale,
-                              int thresholding, int32_t q_lo, int32_t q_hi, float q_w, void* stream) {
+extern "C" int b200_ddpm_step(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs, int32_t* slots, int R, int B,
+                              int64_t chw, float cond_scale, int objective, int thresholding, int32_t q_lo, int32_t q_hi, float q_w,
+                              void* stream) {
+  return b200_ddpm_step_sc(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, thresholding, q_lo, q_hi, q_w, nullptr, stream);
+}
+
+extern "C" int b200_edm_phase_sc(int phase, float* x, float* x_hat, float* x1, float* d, float* net_in, const float* pred, const float* eps,
+                                 const b200_edm_coef* coefs, int32_t* step_ctr, int32_t* slots, int R, int B, int64_t chw, float cond_scale,
+                                 int thresholding, int32_t q_lo, int32_t q_hi, float q_w, float* denoised_out, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(phase >= 0 && phase <= 2, "edm_phase: bad phase");
   B200_REQUIRE(x && x_hat && x1 && d && net_in && coefs && step_ctr && slots, "edm_phase: null pointer");
@@ -308,9 +318,17 @@ extern "C" int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, floa
     edm_commit_step_kernel<<<1, 1, 0, st>>>(step_ctr);
     B200_LAUNCH_OK();
   }
-  edm_phase_kernel<<<B, SMP_THREADS, smem, st>>>(phase, x, x_hat, x1, d, net_in, pred, eps, coefs, step_ctr, slots, R, B, chw, cond_scale, q);
+  edm_phase_kernel<<<B, SMP_THREADS, smem, st>>>(phase, x, x_hat, x1, d, net_in, pred, eps, coefs, step_ctr, slots, R, B, chw, cond_scale, q,
+                                                 denoised_out);
   B200_LAUNCH_OK();
   return B200_OK;
+}
+
+extern "C" int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, float* d, float* net_in, const float* pred, const float* eps,
+                              const b200_edm_coef* coefs, int32_t* step_ctr, int32_t* slots, int R, int B, int64_t chw, float cond_scale,
+                              int thresholding, int32_t q_lo, int32_t q_hi, float q_w, void* stream) {
+  return b200_edm_phase_sc(phase, x, x_hat, x1, d, net_in, pred, eps, coefs, step_ctr, slots, R, B, chw, cond_scale, thresholding, q_lo, q_hi,
+                           q_w, nullptr, stream);
 }
 
 extern "C" int b200_inpaint_mix(float* x, const float* known, const uint8_t* mask, const float* noise, float alpha, float sigma, int B, int C,

@@ -138,12 +138,16 @@ class ElucidatedImagen(_SamplerBase):
             lib = plan.lib
             thr = int(bool(dynamic_threshold))
             key = (float(cond_scale), thr, q_lo, q_hi, q_w)
+            sc_ptr = None
+            if unet.self_cond:                                                 # latest denoiser output conditions the next evaluation (:496, :518, :538)
+                plan.sc_in.zero_()
+                sc_ptr = plan.sc_in.data_ptr()
 
             def phase(ph):
-                _lib.check(lib.b200_edm_phase(ph, x.data_ptr(), x_hat.data_ptr(), x1.data_ptr(), d.data_ptr(), net_in.data_ptr(),
-                                              plan.pred.data_ptr(), eps.data_ptr(), coefs.data_ptr(), step_ctr.data_ptr(),
-                                              plan.slots.data_ptr(), R, B, chw, float(cond_scale), thr, q_lo, q_hi, q_w,
-                                              torch.cuda.current_stream(device).cuda_stream), 'b200_edm_phase')
+                _lib.check(lib.b200_edm_phase_sc(ph, x.data_ptr(), x_hat.data_ptr(), x1.data_ptr(), d.data_ptr(), net_in.data_ptr(),
+                                                 plan.pred.data_ptr(), eps.data_ptr(), coefs.data_ptr(), step_ctr.data_ptr(),
+                                                 plan.slots.data_ptr(), R, B, chw, float(cond_scale), thr, q_lo, q_hi, q_w, sc_ptr,
+                                                 torch.cuda.current_stream(device).cuda_stream), 'b200_edm_phase')
 
             def full_step():
                 eps.copy_(torch.randn(shape, device=device))                   # :489 (S_noise applied in phase 0)

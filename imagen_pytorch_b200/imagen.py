@@ -329,14 +329,18 @@ class Imagen(_SamplerBase):
             coef_buf[:T].copy_(coefs)
             lib = plan.lib
             key = (float(cond_scale), objective, bool(dynamic_threshold), q_lo, q_hi, q_w)
+            sc_ptr = None
+            if unet.self_cond:                                                 # x_start of the previous step conditions the next (:2210, :2252)
+                plan.sc_in.zero_()
+                sc_ptr = plan.sc_in.data_ptr()
 
             def one_step():
                 noise.copy_(torch.randn_like(x))                               # :2160 (drawn every step, also the last)
                 plan.launch()
                 st = torch.cuda.current_stream(device).cuda_stream
-                _lib.check(lib.b200_ddpm_step(x.data_ptr(), plan.pred.data_ptr(), noise.data_ptr(), coef_buf.data_ptr(), plan.slots.data_ptr(),
-                                              R, B, chw, float(cond_scale), objective, int(bool(dynamic_threshold)), q_lo, q_hi, q_w, st),
-                           'b200_ddpm_step')
+                _lib.check(lib.b200_ddpm_step_sc(x.data_ptr(), plan.pred.data_ptr(), noise.data_ptr(), coef_buf.data_ptr(), plan.slots.data_ptr(),
+                                                 R, B, chw, float(cond_scale), objective, int(bool(dynamic_threshold)), q_lo, q_hi, q_w,
+                                                 sc_ptr, st), 'b200_ddpm_step')
 
             out = torch.empty(shape, dtype=torch.float32, device=device)
             if not has_inpainting:

@@ -45,7 +45,7 @@ UNET_DEFAULTS = OrderedDict(
 # They raise instead of silently diverging (SURVEY.md section 7 "API edge cases").
 _UNSUPPORTED = dict(
     use_linear_attn=lambda v: any(cast_tuple(v)), use_linear_cross_attn=lambda v: any(cast_tuple(v)),
-    cross_embed_downsample=bool, self_cond=bool, cond_images_channels=lambda v: v > 0,
+    cross_embed_downsample=bool, cond_images_channels=lambda v: v > 0,
     combine_upsample_fmaps=bool, init_conv_to_final_conv_residual=bool,
     pixel_shuffle_upsample=lambda v: not v, attn_dim_head=lambda v: v != 64,
     final_resnet_block=lambda v: not v,
@@ -76,7 +76,8 @@ class UnetArch:
         self.channels_out = g('channels_out') if g('channels_out') is not None else g('channels')
         self.lowres_cond = bool(g('lowres_cond'))
         self.cond_on_text = bool(g('cond_on_text'))
-        self.init_channels = self.channels * (1 + int(self.lowres_cond))
+        self.self_cond = bool(g('self_cond'))
+        self.init_channels = self.channels * (1 + int(self.lowres_cond) + int(self.self_cond))      # :1184
         self.init_dim = g('init_dim') if g('init_dim') is not None else self.dim
         self.dims = [self.init_dim, *[self.dim * m for m in g('dim_mults')]]
         self.in_out = list(zip(self.dims[:-1], self.dims[1:]))

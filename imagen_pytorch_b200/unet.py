@@ -76,6 +76,8 @@ class UnetPlan:
         self.n_ctx = self.ntt + self.n_static
         # per-step state
         self.x_in = self._zeros((B, a.channels, H, W), torch.float32)
+        # self-conditioning input (imagen_pytorch.py:1541-1543): the samplers' step kernels write x_start here, zeros before the first step
+        self.sc_in = self._zeros((B, a.channels, H, W), torch.float32) if a.self_cond else None
         self.lowres_img = self._zeros((B, a.channels, H, W), torch.float32) if a.lowres_cond else None
         self.pred = self._zeros((R, a.channels_out, H, W), torch.float32)
         self.slots = self._zeros((R,), torch.int32)
@@ -348,8 +350,10 @@ class UnetPlan:
         patches = self._new(M0, Kinit)
         stem = []
         self._ops = stem
-        self._add('b200_im2col_init', self.x_in.data_ptr(), a.channels, self.lowres_img.data_ptr() if a.lowres_cond else None,
-                  a.channels if a.lowres_cond else 0, B, H, W, ks, patches.ptr, Kinit)
+        imgs = [self.x_in] + ([self.sc_in] if a.self_cond else []) + ([self.lowres_img] if a.lowres_cond else [])   # cat order :1543, :1551
+        imgs += [None] * (3 - len(imgs))
+        self._add('b200_im2col_init3', *[v for im in imgs for v in ((im.data_ptr(), a.channels) if im is not None else (None, 0))],
+                  B, H, W, ks, patches.ptr, Kinit)
         Wi = torch.zeros(a.init_dim, ks, ks, Cin, device=self.device)
         bi = torch.zeros(a.init_dim, device=self.device)
         row = 0
@@ -639,7 +643,7 @@ class Unet(nn.Module):
         a = self.arch
         self.channels, self.channels_out = a.channels, a.channels_out
         self.lowres_cond, self.cond_on_text = a.lowres_cond, a.cond_on_text
-        self.self_cond = False
+        self.self_cond = a.self_cond
         self.has_cond_image = False
         self.max_text_len = a.max_text_len
         build_param_tree(self, param_table(a))
@@ -687,13 +691,15 @@ class Unet(nn.Module):
         return self._plans[key]
 
     @torch.no_grad()
-    def _run(self, x, time, keep_rows, R, *, lowres_cond_img, lowres_noise_times, text_embeds, text_mask):
+    def _run(self, x, time, keep_rows, R, *, lowres_cond_img, lowres_noise_times, text_embeds, text_mask, self_cond=None):
         B, _, H, W = x.shape
         plan = self.plan(R, B, H, W, B, x.device)
         with torch.cuda.device(x.device):
             plan.prepare(time, text_embeds=text_embeds, text_mask=text_mask, keep=keep_rows, lowres_cond_img=lowres_cond_img,
                          lowres_noise_times=lowres_noise_times, slot_of_row=torch.arange(R, device=x.device) % B)
             plan.x_in.copy_(x.to(torch.float32))
+            if self.self_cond:                                                  # default: zeros_like(x) (:1542)
+                plan.sc_in.zero_() if self_cond is None else plan.sc_in.copy_(self_cond.to(torch.float32))
             plan.launch()
         return plan.pred
 
@@ -702,8 +708,8 @@ class Unet(nn.Module):
                 cond_images=None, self_cond=None, cond_drop_prob=0.):
         assert not (self.lowres_cond and lowres_cond_img is None), 'low resolution conditioning image must be present'
         assert not (self.lowres_cond and lowres_noise_times is None), 'low resolution conditioning noise time must be present'
-        if cond_images is not None or self_cond is not None:
-            raise NotImplementedError('cond_images / self_cond are outside the B200 hot path')
+        if cond_images is not None:
+            raise NotImplementedError('cond_images is outside the B200 hot path')
         B = x.shape[0]
         if cond_drop_prob == 1:
             keep = torch.zeros(B, dtype=torch.bool, device=x.device)
@@ -712,19 +718,19 @@ class Unet(nn.Module):
         else:                                                                   # prob_mask_like (:201-207)
             keep = torch.zeros(B, device=x.device).float().uniform_(0, 1) < (1 - cond_drop_prob)
         out = self._run(x, time, keep, B, lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
-                        text_embeds=text_embeds, text_mask=text_mask)
+                        text_embeds=text_embeds, text_mask=text_mask, self_cond=self_cond)
         return out.clone()
 
     @torch.no_grad()
     def forward_with_cond_scale(self, x, time, *, cond_scale=1., **kwargs):    # :1510-1522
         if cond_scale == 1:
             return self.forward(x, time, **kwargs)
-        if kwargs.get('cond_images') is not None or kwargs.get('self_cond') is not None:
-            raise NotImplementedError('cond_images / self_cond are outside the B200 hot path')
+        if kwargs.get('cond_images') is not None:
+            raise NotImplementedError('cond_images is outside the B200 hot path')
         B = x.shape[0]
         keep = torch.cat((torch.ones(B, dtype=torch.bool, device=x.device), torch.zeros(B, dtype=torch.bool, device=x.device)))
         out = self._run(x, time, keep, 2 * B, lowres_cond_img=kwargs.get('lowres_cond_img'), lowres_noise_times=kwargs.get('lowres_noise_times'),
-                        text_embeds=kwargs.get('text_embeds'), text_mask=kwargs.get('text_mask'))
+                        text_embeds=kwargs.get('text_embeds'), text_mask=kwargs.get('text_mask'), self_cond=kwargs.get('self_cond'))
         logits, null_logits = out[:B], out[B:]
         return null_logits + (logits - null_logits) * cond_scale
 

@@ -171,6 +171,9 @@ int b200_gate_residual(const void* x, int32_t ldx, const float* gate, const void
  * c runs over cat(img0, img1) (lowres concat :1551). */
 int b200_im2col_init(const float* img0, int C0, const float* img1, int C1, int B, int H, int W, int ksize,
                      void* out, int32_t Kpad, void* stream);
+/* the same with a third NCHW source (channel order img0 | img1 | img2): x | self_cond | lowres_cond_img (imagen_pytorch.py:1541-1551) */
+int b200_im2col_init3(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2, int B, int H, int W,
+                      int ksize, void* out, int32_t Kpad, void* stream);
 
 /* Pixel-unshuffle gather of Downsample (imagen_pytorch.py:638): out[b,h,w,(s1,s2,c)] = x[b,2h+s1,2w+s2,c]. */
 int b200_pixel_unshuffle(const void* x, int32_t ldx, int B, int H, int W, int C, void* out, void* stream);
@@ -249,6 +252,11 @@ typedef struct {
 int b200_ddpm_step(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs,
                    int32_t* slots, int R, int B, int64_t chw, float cond_scale, int objective,
                    int thresholding, int32_t q_lo, int32_t q_hi, float q_w, void* stream);
+/* the same; additionally writes the thresholded x_start [B, chw] (the next step's self-conditioning input, imagen_pytorch.py:2252)
+ * when x_start_out != NULL. */
+int b200_ddpm_step_sc(float* x, const float* pred, const float* noise, const b200_ddpm_coef* coefs,
+                      int32_t* slots, int R, int B, int64_t chw, float cond_scale, int objective,
+                      int thresholding, int32_t q_lo, int32_t q_hi, float q_w, float* x_start_out, void* stream);
 
 typedef struct {
   float s_noise;     /* S_noise: eps = s_noise * z                                        */
@@ -275,6 +283,12 @@ int b200_edm_phase(int phase, float* x, float* x_hat, float* x1, float* d, float
                    const float* pred, const float* eps, const b200_edm_coef* coefs, int32_t* step_ctr,
                    int32_t* slots, int R, int B, int64_t chw, float cond_scale, int thresholding,
                    int32_t q_lo, int32_t q_hi, float q_w, void* stream);
+/* the same; phases 1 and 2 additionally write the thresholded denoiser output D [B, chw] (self-conditioning input of the next
+ * network evaluation, elucidated_imagen.py:518, :538) when denoised_out != NULL. */
+int b200_edm_phase_sc(int phase, float* x, float* x_hat, float* x1, float* d, float* net_in,
+                      const float* pred, const float* eps, const b200_edm_coef* coefs, int32_t* step_ctr,
+                      int32_t* slots, int R, int B, int64_t chw, float cond_scale, int thresholding,
+                      int32_t q_lo, int32_t q_hi, float q_w, float* denoised_out, void* stream);
 
 /* RePaint inpainting conditioning (imagen_pytorch.py:2248-2250, :2285-2286): where mask[b, p] != 0 (uint8 [B, HW], shared by the C
  * channels) x <- alpha * known + sigma * noise (q_sample :272-284; noise may be NULL with sigma == 0 for the final paste). */

@@ -235,13 +235,49 @@ def main():
                     inpaint_images=inp_img, inpaint_masks=inp_mask, inpaint_resample_times=2, seed_inpaint=29,
                     outs_inpaint=[o.clone() for o in r_eip]), os.path.join(out_dir, 'edm_options_dim32.pt'))
 
+    # ---------------------------------------------------------------- 5d. self-conditioning (Unet(self_cond=True), imagen_pytorch.py:1541-1543, :2252)
+    sc_kw = dict(base_kw, self_cond=True)
+    usc, sdsc, cfgsc = build('selfcond', sc_kw, 5)
+    xsc = torch.randn(B, 3, 32, 32, generator=g)
+    scin = torch.randn(B, 3, 32, 32, generator=g).clamp(-1, 1)
+    with torch.no_grad():
+        r_sc = usc(xsc, t, text_embeds=te, text_mask=tm, self_cond=scin)
+        r_sc0 = usc(xsc, t, text_embeds=te, text_mask=tm)                       # no self_cond given: zeros
+        o_sc = unet_ref.unet_forward(sdsc, cfgsc, xsc, t, text_embeds=te, text_mask=tm, self_cond=scin)
+        o_sc0 = unet_ref.unet_forward(sdsc, cfgsc, xsc, t, text_embeds=te, text_mask=tm)
+    for name, a, b in (('given', r_sc, o_sc), ('zeros', r_sc0, o_sc0)):
+        d = _maxdiff(a, b)
+        print(f'[unet self_cond {name}] ref-vs-oracle max|d| = {d:.3e}')
+        assert d < 1e-5 * max(1., a.abs().max().item())
+    im_sc = ref.Imagen(unets=ref.Unet(**sc_kw), image_sizes=32, timesteps=4, text_embed_dim=64)
+    im_sc.unets[0].load_state_dict(sdsc)
+    torch.manual_seed(53)
+    r_scs = im_sc.sample(text_embeds=te, cond_scale=2., use_tqdm=False)
+    torch.manual_seed(53)
+    o_scs = sampler_ref.imagen_sample([(sdsc, cfgsc)], (32,), text_embeds=te, timesteps=4, cond_scale=2.)
+    d = _maxdiff(r_scs, o_scs)
+    print(f'[ddpm self_cond sample] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-4
+    el_sc = ref.ElucidatedImagen(unets=ref.Unet(**sc_kw), image_sizes=32, text_embed_dim=64, num_sample_steps=3, sigma_max=2.)
+    el_sc.unets[0].load_state_dict(sdsc)
+    torch.manual_seed(59)
+    r_sce = el_sc.sample(text_embeds=te, cond_scale=2., use_tqdm=False)
+    torch.manual_seed(59)
+    o_sce = sampler_ref.elucidated_sample([(sdsc, cfgsc)], (32,), text_embeds=te, cond_scale=2., hparams=dict(num_sample_steps=3, sigma_max=2.))
+    d = _maxdiff(r_sce, o_sce)
+    print(f'[edm self_cond sample] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-4
+    torch.save(dict(kwargs=sc_kw, wseed=5, x=xsc, t=t, text_embeds=te, text_mask=tm, self_cond=scin, out=r_sc, out_zeros=r_sc0,
+                    timesteps=4, cond_scale=2., seed_ddpm=53, out_ddpm=r_scs, num_sample_steps=3, sigma_max=2., seed_edm=59, out_edm=r_sce),
+               os.path.join(out_dir, 'self_cond_dim32.pt'))
+
     # ---------------------------------------------------------------- 6. schedule / scalar known answers
     tt = torch.tensor([1., .75, .5, .25, 0., 0.2])
     torch.save(dict(t=tt, cosine=ref.imagen_pytorch.alpha_cosine_log_snr(tt), linear=ref.imagen_pytorch.beta_linear_log_snr(tt),
                     edm_sigmas=el.sample_schedule(4, 7, 0.002, 80)), os.path.join(out_dir, 'schedules.pt'))
 
     # ---------------------------------------------------------------- 7. state_dict key/shape contract of the default configs
-    contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr']}
+    contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr'], 'test_selfcond': shapes_out['selfcond']}
     for name, kw in (('base_dim128', dict(dim=128)), ('base_dim32', dict(dim=32, dim_mults=(1, 2, 4, 8)))):
         torch.manual_seed(0)
         m = ref.Unet(**kw)

@@ -96,10 +96,10 @@ def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, con
                        pred_objective='noise', dynamic_thresholding=True, percentile=0.95,
                        unet_kwargs=None, lowres_log_snr=None, trace=None, randn=torch.randn,
                        init_images=None, skip_steps=None, inpaint_images=None, inpaint_masks=None,
-                       inpaint_resample_times=5):
+                       inpaint_resample_times=5, self_cond=False):
     """Imagen.p_sample_loop (imagen_pytorch.py:2167-2289) + p_sample (:2112-2165) +
     p_mean_variance (:2042-2110), incl. init image / skipped steps (:2205-2206, :2230-2231) and RePaint
-    inpainting (:2216-2222, :2245-2279); no self-conditioning.  inpaint_images / init_images arrive already
+    inpainting (:2216-2222, :2245-2279) and self-conditioning on the previous step's thresholded x_start (:2252).  inpaint_images / init_images arrive already
     normalised and resized (prepare_inpaint / the caller), as p_sample_loop's own callers hand them over.
     unet_fn(x, log_snr, cond_scale=..., **unet_kwargs) -> prediction."""
     unet_kwargs = dict(unet_kwargs or {})
@@ -111,14 +111,16 @@ def ddpm_p_sample_loop(unet_fn, shape, *, schedule='cosine', timesteps=1000, con
     has_inpainting = inpaint_images is not None and inpaint_masks is not None
     resample_times = inpaint_resample_times if has_inpainting else 1
     steps = list(sampling_timesteps(timesteps, batch, img.device))[(skip_steps or 0):]   # :2226-2231
+    x_start = None                                                             # :2210 (self conditioning)
     for times, times_next in steps:                                            # :2242
         is_last_timestep = times_next == 0
         for r in reversed(range(resample_times)):
             if has_inpainting:                                                 # :2248-2250
                 noised = q_sample(log_snr_fn, inpaint_images, times, randn(tuple(img.shape)))
                 img = img * ~inpaint_masks + noised * inpaint_masks
+            sc = dict(self_cond=x_start) if self_cond else {}                  # :2252
             pred = unet_fn(img, log_snr_fn(times), cond_scale=cond_scale,
-                           lowres_noise_times=lowres_log_snr, **unet_kwargs)   # :2072-2083
+                           lowres_noise_times=lowres_log_snr, **sc, **unet_kwargs)   # :2072-2083
             pad = lambda v: v.view(-1, 1, 1, 1)
             alpha, sigma = log_snr_to_alpha_sigma(pad(log_snr_fn(times)))
             if pred_objective == 'noise':                                      # :314-318
@@ -192,7 +194,7 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
                                  timesteps=timesteps[i], cond_scale=cond_scale[i],
                                  pred_objective=pred_objectives[i],
                                  dynamic_thresholding=dynamic_thresholding[i], unet_kwargs=kw,
-                                 lowres_log_snr=lowres_log_snr, trace=trace, randn=randn, **opt)
+                                 lowres_log_snr=lowres_log_snr, trace=trace, randn=randn, self_cond=cfg.get('self_cond', False), **opt)
         outputs.append(img)
         if stop_at_unet_number is not None and stop_at_unet_number == i + 1:
             break
@@ -229,7 +231,8 @@ def edm_precond_forward(unet_fn, x, sigma, *, sigma_data, dynamic_thresholding=T
 def edm_one_unet_sample(unet_fn, shape, *, num_sample_steps=32, sigma_min=0.002, sigma_max=80, sigma_data=0.5,
                         rho=7, S_churn=80, S_tmin=0.05, S_tmax=50, S_noise=1.003, cond_scale=1.,
                         dynamic_thresholding=True, unet_kwargs=None, trace=None, randn=torch.randn,
-                        init_images=None, skip_steps=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5):
+                        init_images=None, skip_steps=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5,
+                        self_cond=False):
     """ElucidatedImagen.one_unet_sample, elucidated_imagen.py:392-545 (init image :446-447, skipped steps :476-477, RePaint
     inpainting :455-462, :498-499, :533-536, :541-542; inpaint / init images arrive normalised and resized)."""
     unet_kwargs = dict(unet_kwargs or {})
@@ -243,6 +246,7 @@ def edm_one_unet_sample(unet_fn, shape, *, num_sample_steps=32, sigma_min=0.002,
     resample_times = inpaint_resample_times if has_inpainting else 1
     kw = dict(sigma_data=sigma_data, dynamic_thresholding=dynamic_thresholding, cond_scale=cond_scale, **unet_kwargs)
     steps = list(zip(sigmas[:-1], sigmas[1:], gammas[:-1]))[(skip_steps or 0):]   # :476-477
+    x_start = None                                                             # :451 (self conditioning)
     for ind, (sigma, sigma_next, gamma) in enumerate(steps):
         is_last_timestep = ind == len(steps) - 1
         sigma, sigma_next, gamma = (t.item() for t in (sigma, sigma_next, gamma))   # :484
@@ -253,16 +257,19 @@ def edm_one_unet_sample(unet_fn, shape, *, num_sample_steps=32, sigma_min=0.002,
             images_hat = images + added_noise
             if has_inpainting:                                                 # :498-499
                 images_hat = images_hat * ~inpaint_masks + (inpaint_images + added_noise) * inpaint_masks
-            model_output = edm_precond_forward(unet_fn, images_hat, sigma_hat, **kw)
+            sc = dict(self_cond=x_start) if self_cond else {}                  # :496
+            model_output = edm_precond_forward(unet_fn, images_hat, sigma_hat, **sc, **kw)
             d = (images_hat - model_output) / sigma_hat
             images_next = images_hat + (sigma_next - sigma_hat) * d
             if sigma_next != 0:                                                # :515-529
-                model_output_next = edm_precond_forward(unet_fn, images_next, sigma_next, **kw)
+                sc = dict(self_cond=model_output) if self_cond else {}         # :518
+                model_output_next = edm_precond_forward(unet_fn, images_next, sigma_next, **sc, **kw)
                 d_prime = (images_next - model_output_next) / sigma_next
                 images_next = images_hat + 0.5 * (sigma_next - sigma_hat) * (d + d_prime)
             images = images_next
             if has_inpainting and not (r == 0 or is_last_timestep):           # :533-536
                 images = images + (sigma - sigma_next) * randn(shape)
+            x_start = model_output if sigma_next == 0 else model_output_next   # :538
             if trace is not None:
                 trace.append(images.clone())
     images = images.clamp(-1., 1.)
@@ -302,6 +309,7 @@ def elucidated_sample(unets, image_sizes, *, text_embeds, text_masks=None, cond_
         fn = lambda x, t, cond_scale, _sd=sd, _cfg=cfg, **k: \
             unet_ref.unet_forward_with_cond_scale(_sd, _cfg, x, t, cond_scale=cond_scale, **k)
         img = edm_one_unet_sample(fn, (batch, cfg['channels'], size, size), cond_scale=cond_scale[i],
-                                  dynamic_thresholding=dynamic_thresholding, unet_kwargs=kw, trace=trace, randn=randn, **hp, **opt)
+                                  dynamic_thresholding=dynamic_thresholding, unet_kwargs=kw, trace=trace, randn=randn,
+                                  self_cond=cfg.get('self_cond', False), **hp, **opt)
         outputs.append(img)
     return outputs if return_all_unet_outputs else img

@@ -37,7 +37,7 @@ def unet_config(**kw):
         init_conv_kernel_size=7, attn_pool_text=True, attn_pool_num_latents=32,
         memory_efficient=False, use_global_context_attn=True,
         scale_skip_connection=True, final_resnet_block=True,
-        final_conv_kernel_size=3, pixel_shuffle_upsample=True,
+        final_conv_kernel_size=3, pixel_shuffle_upsample=True, self_cond=False,
     )
     for k, v in kw.items():
         cfg[k] = v
@@ -247,10 +247,10 @@ def _upsample(x, sd, p, pixel_shuffle):               # PixelShuffleUpsample :60
 
 
 def unet_forward(sd, cfg, x, time, *, text_embeds=None, text_mask=None,
-                 lowres_cond_img=None, lowres_noise_times=None, cond_drop_prob=0.):
-    """Unet.forward, imagen_pytorch.py:1524-1725 (self_cond / cond_images /
-    combine_upsample_fmaps / init_conv_to_final_conv_residual branches omitted:
-    out of scope per SURVEY.md section 8a; the product rejects them too)."""
+                 lowres_cond_img=None, lowres_noise_times=None, cond_drop_prob=0., self_cond=None):
+    """Unet.forward, imagen_pytorch.py:1524-1725 (cond_images / combine_upsample_fmaps /
+    init_conv_to_final_conv_residual branches omitted: out of scope per SURVEY.md section 8a;
+    the product rejects them too)."""
     heads = cfg['attn_heads']
     batch = x.shape[0]
     nlev = len(cfg['dim_mults'])
@@ -258,6 +258,8 @@ def unet_forward(sd, cfg, x, time, *, text_embeds=None, text_mask=None,
     layer_attns = _tup(cfg['layer_attns'], nlev)
     mem_eff = cfg['memory_efficient']
 
+    if cfg.get('self_cond', False):                                            # :1541-1543
+        x = torch.cat((x, torch.zeros_like(x) if self_cond is None else self_cond), dim=1)
     assert not (cfg['lowres_cond'] and lowres_cond_img is None)
     if lowres_cond_img is not None:
         x = torch.cat((x, lowres_cond_img), dim=1)                             # :1550-1551

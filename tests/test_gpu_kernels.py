@@ -337,6 +337,15 @@ def test_layout_gathers():
     cols = F.unfold(x, ks, padding=ks // 2).view(B, Cin, ks * ks, H * W).permute(0, 3, 2, 1).reshape(B * H * W, ks * ks * Cin)
     torch.cuda.synchronize()
     assert torch.equal(out[:, :ks * ks * Cin], cols.to(BF16)) and out[:, ks * ks * Cin:].abs().max() == 0
+    # three sources: x | self_cond | lowres_cond_img (imagen_pytorch.py:1541-1551)
+    img2 = rnd(B, 3, H, W, seed=2)
+    K3 = ops.ceil_to(ks * ks * 9, 64)
+    out3 = torch.zeros(B * H * W, K3, dtype=BF16, device=DEV)
+    _lib.call('b200_im2col_init3', img0.data_ptr(), 3, img1.data_ptr(), 3, img2.data_ptr(), 3, B, H, W, ks, out3.data_ptr(), K3, stream())
+    x3 = torch.cat((img0, img1, img2), dim=1)
+    cols3 = F.unfold(x3, ks, padding=ks // 2).view(B, 9, ks * ks, H * W).permute(0, 3, 2, 1).reshape(B * H * W, ks * ks * 9)
+    torch.cuda.synchronize()
+    assert torch.equal(out3[:, :ks * ks * 9], cols3.to(BF16)) and out3[:, ks * ks * 9:].abs().max() == 0
     xr = rnd(B, H, W, 16).to(BF16)
     o2 = torch.zeros(B * (H // 2) * (W // 2), 64, dtype=BF16, device=DEV)
     _lib.call('b200_pixel_unshuffle', xr.data_ptr(), 16, B, H, W, 16, o2.data_ptr(), stream())
@@ -458,3 +467,10 @@ def test_quantile_threshold_exact_against_torch_quantile():
     torch.cuda.synchronize()
     s = torch.quantile(x0.flatten(1).abs(), 0.95, dim=-1).clamp(min=1.).view(-1, 1, 1, 1)
     assert_close(x, x0.clamp(-s, s) / s, rtol=2.5e-7, atol=0, what='threshold (1 ulp: lerp FMA contraction inside ATen)')
+    # the self-conditioning variant additionally exports the thresholded x_start (here identical to the step's output)
+    x2, xs = x0.clone(), torch.full_like(x0, float('nan'))
+    slots.zero_()
+    _lib.call('b200_ddpm_step_sc', x2.data_ptr(), zeros.data_ptr(), zeros.data_ptr(), coefs.data_ptr(), slots.data_ptr(), B, B, chw, 1.0, 0, 1, q[0], q[1],
+              q[2], xs.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(x2, x) and torch.equal(xs, x)

@@ -231,6 +231,36 @@ def test_elucidated_sampler_options_match_oracle_with_shared_noise():
     assert torch.equal(o_inp[1].cpu()[m], known)
 
 
+def test_self_conditioning_forward_and_samplers():
+    """Unet(self_cond=True): forward against the reference goldens (given / default-zero self_cond) and both samplers
+    feeding the step kernels' x_start back into the stem, against the oracle on the same noise."""
+    g = load_golden('self_cond_dim32.pt')
+    u = make_unet(g['kwargs'], 'test_selfcond', g['wseed'])
+    model = (synth_weights('test_selfcond', g['wseed']), unet_ref.unet_config(**g['kwargs']))
+    kw = dict(text_embeds=g['text_embeds'].to(DEV), text_mask=g['text_mask'].to(DEV))
+    a = u(g['x'].to(DEV), g['t'].to(DEV), self_cond=g['self_cond'].to(DEV), **kw)
+    b = u(g['x'].to(DEV), g['t'].to(DEV), **kw)
+    ea, eb = rel_err(a, g['out']), rel_err(b, g['out_zeros'])
+    assert ea < 3e-2 and eb < 3e-2
+    te = g['text_embeds']
+    im = b2.Imagen(u, image_sizes=32, timesteps=g['timesteps'], text_embed_dim=64).to(DEV)
+    torch.manual_seed(61)
+    o1 = im.sample(text_embeds=te.to(DEV), cond_scale=g['cond_scale'], use_tqdm=False)
+    torch.manual_seed(61)
+    with torch.no_grad():
+        r1 = sampler_ref.imagen_sample([model], (32,), text_embeds=te, timesteps=g['timesteps'], cond_scale=g['cond_scale'], randn=cuda_randn)
+    el = b2.ElucidatedImagen(u, image_sizes=32, text_embed_dim=64, num_sample_steps=g['num_sample_steps'], sigma_max=g['sigma_max']).to(DEV)
+    torch.manual_seed(67)
+    o2 = el.sample(text_embeds=te.to(DEV), cond_scale=g['cond_scale'], use_tqdm=False)
+    torch.manual_seed(67)
+    with torch.no_grad():
+        r2 = sampler_ref.elucidated_sample([model], (32,), text_embeds=te, cond_scale=g['cond_scale'],
+                                           hparams=dict(num_sample_steps=g['num_sample_steps'], sigma_max=g['sigma_max']), randn=cuda_randn)
+    d1, d2 = (o1.cpu() - r1).abs().mean().item(), (o2.cpu() - r2).abs().mean().item()
+    record('self_cond', fwd_given=ea, fwd_zeros=eb, ddpm_mean_abs=d1, edm_mean_abs=d2)
+    assert d1 < 1e-2 and d2 < 3e-2
+
+
 def test_cuda_graph_replay_equals_eager_loop_bit_for_bit(monkeypatch):
     """Same kernels, same graph-safe Philox draws: the captured t-loop must reproduce the eager loop exactly."""
     g = load_golden('ddpm_sample_dim32.pt')

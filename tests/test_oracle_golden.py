@@ -115,6 +115,25 @@ def test_edm_sampler_options_match_reference_golden():
     assert torch.equal(b[1][m], ((g['inpaint_images'] * 2 - 1 + 1) * 0.5)[m])
 
 
+def test_self_conditioning_matches_reference_golden():
+    """Unet(self_cond=True): forward with a given / default (zeros) self_cond, and both samplers feeding x_start back
+    (imagen_pytorch.py:1541-1543, :2252; elucidated_imagen.py:496, :518, :538)."""
+    g = load_golden('self_cond_dim32.pt')
+    sd, cfg = synth_weights('test_selfcond', g['wseed']), unet_ref.unet_config(**g['kwargs'])
+    kw = dict(text_embeds=g['text_embeds'], text_mask=g['text_mask'])
+    with torch.no_grad():
+        a = unet_ref.unet_forward(sd, cfg, g['x'], g['t'], self_cond=g['self_cond'], **kw)
+        b = unet_ref.unet_forward(sd, cfg, g['x'], g['t'], **kw)
+        torch.manual_seed(g['seed_ddpm'])
+        c = sampler_ref.imagen_sample([(sd, cfg)], (32,), text_embeds=g['text_embeds'], timesteps=g['timesteps'], cond_scale=g['cond_scale'])
+        torch.manual_seed(g['seed_edm'])
+        d = sampler_ref.elucidated_sample([(sd, cfg)], (32,), text_embeds=g['text_embeds'], cond_scale=g['cond_scale'],
+                                          hparams=dict(num_sample_steps=g['num_sample_steps'], sigma_max=g['sigma_max']))
+    assert (a - g['out']).abs().max() < 1e-4 and (b - g['out_zeros']).abs().max() < 1e-4
+    assert (a - b).abs().max() > 1e-2                      # the self-conditioning channels matter
+    assert (c - g['out_ddpm']).abs().max() < 1e-4 and (d - g['out_edm']).abs().max() < 1e-3
+
+
 def test_schedule_known_answers():
     g = load_golden('schedules.pt')
     assert torch.allclose(sampler_ref.alpha_cosine_log_snr(g['t']), g['cosine'], atol=1e-6)

@@ -12,6 +12,7 @@ CASES = {
     'test_base': dict(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24),
     'test_sr': dict(dim=32, dim_mults=(1, 2, 4), text_embed_dim=64, max_text_len=24, num_resnet_blocks=(1, 2, 2),
                     layer_attns=(False, False, True), layer_cross_attns=(False, False, True), memory_efficient=True, lowres_cond=True),
+    'test_selfcond': dict(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24, self_cond=True),
 }
 
 
@@ -41,7 +42,7 @@ def test_fresh_unet_final_conv_is_zero_like_reference():
     assert u.final_conv.weight.abs().max() == 0 and u.final_conv.bias.abs().max() == 0   # zero_init_ :1438
 
 
-@pytest.mark.parametrize('kw', [dict(use_linear_attn=True), dict(self_cond=True), dict(cond_images_channels=3), dict(attn_dim_head=32),
+@pytest.mark.parametrize('kw', [dict(use_linear_attn=True), dict(init_conv_to_final_conv_residual=True), dict(cond_images_channels=3), dict(attn_dim_head=32),
                                 dict(pixel_shuffle_upsample=False), dict(combine_upsample_fmaps=True), dict(cross_embed_downsample=True)])
 def test_unsupported_options_raise_instead_of_diverging(kw):
     with pytest.raises(NotImplementedError):
