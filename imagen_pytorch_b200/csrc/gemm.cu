@@ -411,12 +411,12 @@ __device__ __forceinline__ void tma_store_wait_read(int lane, int debug) {
   __syncwarp();
 }
 
-template <int BNW, class Load32, class Wait32>
+template <int BNW, bool PIPE, class Load32, class Wait32>
 __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUtensorMap* mapO, const RowInfo& ri, int n0, uint32_t stage, uint32_t meta,
                                                 int lane, Load32 load32, Wait32 wait32) {
   static_assert(BNW % 32 == 0, "staged epilogue works on 32-column groups");
   const EpiDev& e = p.epi;
-  float va[32], vb[32];
+  float va[32];
   if (e.l2_cols > 0) {
     // F.normalize over 64-column heads: pass 1 = sum of squares of the activated values, pass 2 = reload, scale, stage.
     // (the scale is applied in fp32 before the single bf16 rounding)
@@ -464,6 +464,27 @@ __device__ __forceinline__ void epilogue_staged(const GemmParams& p, const CUten
     }
     return;
   }
+  if constexpr (!PIPE) {
+    // 16 epilogue warps (4 per scheduler): thread-level parallelism hides the tcgen05.ld latency, one register buffer is enough
+#pragma unroll 1
+    for (int g0 = 0; g0 < BNW; g0 += 32) {
+      const int ng = n0 + g0;
+      if (ng >= p.N) break;
+      load32(g0, va);
+      wait32(va);
+      epi_math32(e, ng, va);
+      if (p.tma_store) {
+        tma_store_wait_read(lane, p.debug);
+        stage32(va, stage, lane);
+        flush32_tma(mapO, ri, ng, stage, lane, p.debug);
+      } else {
+        stage32(va, stage, lane);
+        flush32(p, ri, ng, stage, meta, lane);
+      }
+    }
+    return;
+  }
+  float vb[32];
   load32(0, va);
 #pragma unroll 1
   for (int g0 = 0; g0 < BNW; g0 += 64) {
@@ -517,8 +538,8 @@ __device__ __forceinline__ void tmem_wait_regs16(float* v) {
 // tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 
-template <int BN, int STAGES, bool STAGED>
-__global__ void __launch_bounds__(64 + 32 * (BN >= 128 ? 8 : 4), 1)
+template <int BN, int STAGES, bool STAGED, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO, const __grid_constant__ GemmParams p) {
@@ -552,7 +573,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], BN >= 128 ? 8 : 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], NEPI);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -629,11 +650,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     }
   } else {
-    // ---------------- epilogue warps: TMEM lane quarter = warp % 4.  Tiles of >= 128 columns get EIGHT epilogue warps (two per
-    // lane quarter, each owning half of the columns): epilogue-heavy GEMMs (small K, GELU, L2 norm) were bound by the four
-    // warps' instruction issue (ncu: FF1 with erf-GELU spent half its time in the epilogue math).
-    constexpr int HALVES = BN >= 128 ? 2 : 1;
+    // ---------------- epilogue warps: TMEM lane quarter = warp % 4, NEPI / 4 warps per quarter, each owning BN / (NEPI / 4) columns.
+    // 4 warps for narrow tiles, 8 for >= 128 columns, 16 for the small-K GEMMs whose time IS the epilogue: with 2 warps per
+    // scheduler the epilogue runs at CPI ~6 per warp (dependent tcgen05.ld -> convert -> st.shared chains), more warps hide it.
+    constexpr int HALVES = NEPI / 4;
     constexpr int BNH = BN / HALVES;
+    static_assert(BNH >= 32 && BNH % 32 == 0, "each epilogue warp needs at least one 32-column group");
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const RowInTile rit = row_in_tile(p, q * 32 + lane);
@@ -648,7 +670,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       if (!(p.debug & 1)) {
         if constexpr (STAGED) {
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
-          epilogue_staged<BNH>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
+          epilogue_staged<BNH, (NEPI <= 8)>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
                                [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
                                [&](float* v) { tmem_wait_regs32(v); });
         } else {
@@ -809,7 +831,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       if (!(p.debug & 1)) {
         if constexpr (STAGED) {
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
-          epilogue_staged<BNH>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
+          epilogue_staged<BNH, true>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
                                [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
                                [&](float* v) { tmem_wait_regs32(v); });
         } else {
@@ -897,18 +919,18 @@ int next_pow2(int v) {
   return r;
 }
 
-template <int BN, int STAGES, bool SIMPLE>
+template <int BN, int STAGES, bool SIMPLE, int NEPI>
 int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + (BN >= 128 ? 8 : 4) * EPI_STAGE_BYTES : 0) /*staging*/;
+  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + NEPI * EPI_STAGE_BYTES : 0) /*staging*/;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const long long total = (long long)ntiles * (p.Npad / BN);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES, SIMPLE><<<grid, 64 + 32 * (BN >= 128 ? 8 : 4), smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
+  conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }
@@ -928,9 +950,26 @@ bool gemm_is_simple(const GemmParams& p) {
   return (long long)p.B * p.H * p.W < (1ll << 31);
 }
 
+// B200_IMAGEN_GEMM_EPI16=1 moves the small-K GEMMs to the 16-epilogue-warp kernels (opt-in until measured on B200)
+bool epi16_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_IMAGEN_GEMM_EPI16");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
+
 template <int BN, int STAGES>
 int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
-  return gemm_is_simple(p) ? launch_tc2<BN, STAGES, true>(maps, mapB, mapO, p, ntiles, st) : launch_tc2<BN, STAGES, false>(maps, mapB, mapO, p, ntiles, st);
+  constexpr int NEPI = BN >= 128 ? 8 : 4;
+  if (!gemm_is_simple(p)) return launch_tc2<BN, STAGES, false, NEPI>(maps, mapB, mapO, p, ntiles, st);
+  if constexpr (BN >= 128) {
+    // K <= 512: a tile's MMAs take ~1-4k cycles, its epilogue ~8k with 8 warps -> 16 epilogue warps, shallower operand ring.
+    // (the per-head L2 norm needs 64 columns per warp: 16 warps only at BN = 256)
+    if (epi16_enabled() && p.total_chunks <= 8 && (p.epi.l2_cols == 0 || BN == 256))
+      return launch_tc2<BN, (BN == 256 ? 3 : 4), true, 16>(maps, mapB, mapO, p, ntiles, st);
+  }
+  return launch_tc2<BN, STAGES, true, NEPI>(maps, mapB, mapO, p, ntiles, st);
 }
 
 template <int BN, int STAGES, bool SIMPLE>

@@ -40,6 +40,24 @@ def test_ddpm_coefficient_table_matches_oracle_posterior(schedule):
     assert coefs[-1, 5] == 0            # no noise on the last step
 
 
+@pytest.mark.parametrize('schedule', ['cosine', 'linear'])
+def test_repaint_coefficient_table_matches_oracle_q_sample(schedule):
+    """(alpha_t, sigma_t) of q_sample and (c1, c2, alpha_from) of q_sample_from_to, as b200_inpaint_mix / b200_renoise consume them:
+    x*c1 + (noise*c2)/alpha_from must reproduce the oracle's q_sample_from_to(x, t_next -> t) bit for bit."""
+    T = 6
+    sched = GaussianDiffusionContinuousTimes(noise_schedule=schedule, timesteps=T)
+    rp = sched.repaint_coefficients('cpu')
+    fn = sampler_ref.LOG_SNR[schedule]
+    g = torch.Generator().manual_seed(3)
+    x, noise = torch.randn(2, 3, 4, 4, generator=g), torch.randn(2, 3, 4, 4, generator=g)
+    steps = list(sampler_ref.sampling_timesteps(T, 2))
+    for i, (t, t_next) in enumerate(steps):
+        a, s_, c1, c2, af = rp[i]
+        assert torch.equal(a * x + s_ * noise, sampler_ref.q_sample(fn, x, t, noise))
+        if i < T - 1:                                            # the last step (t_next = 0) is never re-noised (:2271)
+            assert torch.equal(x * c1 + (noise * c2) / af, sampler_ref.q_sample_from_to(fn, x, t_next, t, noise))
+
+
 def test_edm_tables_match_oracle_schedule():
     u = Unet(dim=32, dim_mults=(1, 2), text_embed_dim=64)
     el = ElucidatedImagen(u, image_sizes=16, text_embed_dim=64, num_sample_steps=5)

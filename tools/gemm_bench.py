@@ -50,7 +50,8 @@ def child():
                                          bias=ops.padded_bias(torch.zeros(512, device=dev), 512, dev), act=_lib.ACT_SILU),
     }
     st = torch.cuda.current_stream(dev)
-    tag = f"pair={os.environ.get('B200_IMAGEN_GEMM_PAIR', '0')} tma_store={os.environ.get('B200_IMAGEN_GEMM_TMA_STORE', '1')} debug={os.environ.get('B200_IMAGEN_GEMM_DEBUG', '0')}"
+    tag = (f"pair={os.environ.get('B200_IMAGEN_GEMM_PAIR', '0')} tma_store={os.environ.get('B200_IMAGEN_GEMM_TMA_STORE', '1')} "
+           f"epi16={os.environ.get('B200_IMAGEN_GEMM_EPI16', '1')} debug={os.environ.get('B200_IMAGEN_GEMM_DEBUG', '0')}")
     only = os.environ.get('GEMM_BENCH_ONLY')
     for name, (call, flops, keep) in cases.items():
         if only and only not in name:
@@ -74,6 +75,6 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'child':
         child()
     else:
-        for tma, dbg in (('1', '0'), ('1', '8'), ('1', '24'), ('1', '14'), ('1', '30')):
-            env = dict(os.environ, B200_IMAGEN_GEMM_TMA_STORE=tma, B200_IMAGEN_GEMM_DEBUG=dbg)
+        for epi16, dbg in (('1', '0'), ('0', '0'), ('1', '6'), ('0', '6')):
+            env = dict(os.environ, B200_IMAGEN_GEMM_EPI16=epi16, B200_IMAGEN_GEMM_DEBUG=dbg)
             subprocess.run([sys.executable, __file__, 'child'], env=env, check=False)
