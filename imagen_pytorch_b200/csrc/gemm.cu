@@ -950,11 +950,12 @@ bool gemm_is_simple(const GemmParams& p) {
   return (long long)p.B * p.H * p.W < (1ll << 31);
 }
 
-// B200_IMAGEN_GEMM_EPI16=1 moves the small-K GEMMs to the 16-epilogue-warp kernels (opt-in until measured on B200)
+// B200_IMAGEN_GEMM_EPI16=0 keeps the small-K GEMMs on the 8-epilogue-warp kernels (A/B comparisons; measured on B200 with 16 warps:
+// to_q + L2 norm 61 -> 49 us, FF1 + GELU 53 -> 45 us, plain 131072x128->512 41 -> 39 us, K = 512 linears 5 % slower -> K <= 256 only)
 bool epi16_enabled() {
   static const bool on = [] {
     const char* e = getenv("B200_IMAGEN_GEMM_EPI16");
-    return e != nullptr && atoi(e) != 0;
+    return e == nullptr || atoi(e) != 0;
   }();
   return on;
 }
@@ -964,9 +965,9 @@ int launch_tc(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMa
   constexpr int NEPI = BN >= 128 ? 8 : 4;
   if (!gemm_is_simple(p)) return launch_tc2<BN, STAGES, false, NEPI>(maps, mapB, mapO, p, ntiles, st);
   if constexpr (BN >= 128) {
-    // K <= 512: a tile's MMAs take ~1-4k cycles, its epilogue ~8k with 8 warps -> 16 epilogue warps, shallower operand ring.
+    // K <= 256: a tile's MMAs take ~1-2k cycles, its epilogue ~8k with 8 warps -> 16 epilogue warps, shallower operand ring.
     // (the per-head L2 norm needs 64 columns per warp: 16 warps only at BN = 256)
-    if (epi16_enabled() && p.total_chunks <= 8 && (p.epi.l2_cols == 0 || BN == 256))
+    if (epi16_enabled() && p.total_chunks <= 4 && (p.epi.l2_cols == 0 || BN == 256))
       return launch_tc2<BN, (BN == 256 ? 3 : 4), true, 16>(maps, mapB, mapO, p, ntiles, st);
   }
   return launch_tc2<BN, STAGES, true, NEPI>(maps, mapB, mapO, p, ntiles, st);
