@@ -70,6 +70,29 @@ def test_unet_sr_forward_matches_reference_golden():
     assert e < 3e-2                                        # measured 8.1e-3
 
 
+@pytest.mark.parametrize('B,size', [(1, 24), (3, 40)])
+def test_unet_forward_odd_shapes_match_oracle(B, size):
+    """Ragged cases: odd batch sizes, image sizes that are not powers of two (3x3 / 5x5 pixels at the coarsest level: TMA boxes
+    hang over the image, attention tiles are partial), a text mask with an all-False row and one with a single token."""
+    g = load_golden('unet_base_dim32.pt')
+    u = make_unet(g['kwargs'], 'test_base', g['wseed'])
+    sd, cfg = synth_weights('test_base', g['wseed']), unet_ref.unet_config(**g['kwargs'])
+    gen = torch.Generator().manual_seed(100 + size)
+    x = torch.randn(B, 3, size, size, generator=gen)
+    t = torch.linspace(-2.0, 1.5, B)
+    te = torch.randn(B, 24, 64, generator=gen)
+    tm = torch.ones(B, 24, dtype=torch.bool)
+    tm[0, :] = False                                        # no text at all for sample 0
+    if B > 1:
+        tm[1, 1:] = False                                   # a single token
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, cfg, x, t, text_embeds=te, text_mask=tm)
+    out = u(x.to(DEV), t.to(DEV), text_embeds=te.to(DEV), text_mask=tm.to(DEV))
+    e = rel_err(out, ref)
+    record(f'unet_odd_B{B}_{size}px', rel=e)
+    assert out.shape == ref.shape and e < 3e-2
+
+
 def test_tcgen05_path_equals_simt_checker_on_the_whole_unet():
     g = load_golden('unet_base_dim32.pt')
     u = make_unet(g['kwargs'], 'test_base', g['wseed'])
