@@ -59,6 +59,7 @@ SIGNATURES = {
     'b200_check_device': [_I],
     'b200_sizeof': [_I],
     'b200_conv_gemm_npad': [_I],
+    'b200_conv_gemm_splitk': [_I, _I, _I, _I, _I],
     'b200_conv_gemm': [C.POINTER(Src), _I, C.POINTER(Seg), _I, _I, _I, _I, _P, _I, C.POINTER(Epilogue), _I, _P, _P],
     'b200_attention': [_P, _P, _L, _L, _I, _I, _P, _P, _L, _L, _I, _I, _I, _I, _F, _P],
     'b200_rmsnorm_film_silu': [C.POINTER(Src), _I, _F, _P, _P, _I, _I, _P, _I, _L, _P],

@@ -45,6 +45,7 @@ struct GemmParams {
   int tiles_w, tiles_h;
   int N, Npad;
   int nseg, total_chunks, ntiles_m;
+  int ksplit;      // > 1: K is split over ksplit adjacent work items; each writes its raw fp32 partial tile to out + split * M * ldc
   int tma_store;   // staged epilogue hands each 32-row x 32-column group to a TMA store (plain bf16 row-major destinations)
   int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads, 8 no wait before restaging (WRONG results), 16 no proxy fence (WRONG results)
   int nchunks[B200_MAX_SRC];
@@ -558,7 +559,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = p.Npad / BN;
-  const int total_tiles = p.ntiles_m * n_tiles_n;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int total_tiles = p.ntiles_m * n_tiles_n * ksplit;   // work items: (row tile, column tile, K split), the split index fastest
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -591,7 +593,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tile = t / n_tiles_n, n0 = (t % n_tiles_n) * BN;
+        const int split = t % ksplit, tt = t / ksplit;
+        const int kc0 = split * p.total_chunks / ksplit, kc1 = (split + 1) * p.total_chunks / ksplit;
+        const int tile = tt / n_tiles_n, n0 = (tt % n_tiles_n) * BN;
         const int wblk = tile % p.tiles_w;
         const int hblk = (tile / p.tiles_w) % p.tiles_h;
         const int bblk = tile / (p.tiles_w * p.tiles_h);
@@ -603,6 +607,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int dh = p.seg[s].dh, dw = p.seg[s].dw;
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
+            if (kc < kc0 || kc >= kc1) continue;   // another split's share of K
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (p.debug & 4) {
               mbar_arrive(&full_bar[stage]);
@@ -628,7 +633,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-        for (int kc = 0; kc < p.total_chunks; ++kc) {
+        const int split = t % ksplit;
+        const int nkc = (split + 1) * p.total_chunks / ksplit - split * p.total_chunks / ksplit;
+        for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
@@ -662,8 +669,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int tile = (int)((unsigned)t / (unsigned)n_tiles_n), n0 = (t - tile * n_tiles_n) * BN;
-      const RowInfo ri = tile_row(p, tile, rit);
+      const int tt = (int)((unsigned)t / (unsigned)ksplit), split = t - tt * ksplit;
+      const int tile = (int)((unsigned)tt / (unsigned)n_tiles_n), n0 = (tt - tile * n_tiles_n) * BN;
+      RowInfo ri = tile_row(p, tile, rit);
+      if (p.ksplit > 1) ri.orow += (long long)split * p.B * p.H * p.W;   // partial tiles: [split][row][col] fp32
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
@@ -911,6 +920,52 @@ __global__ void conv_gemm_ref_epilogue_kernel(GemmParams p, const float* __restr
   }, [](float*) {});
 }
 
+// split-K finish: out = epilogue(sum_s partial[s]) -- partials are added in split order, so the result does not depend on timing
+template <int BNW>
+__global__ void conv_gemm_splitk_epilogue_kernel(GemmParams p, const float* __restrict__ scratch, int ksplit) {
+  const long long M = (long long)p.B * p.H * p.W;
+  const int chunks = p.Npad / BNW;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * chunks) return;
+  const int ch = (int)(idx % chunks);
+  const long long m = idx / chunks;
+  RowInfo ri;
+  ri.valid = true;
+  ri.w = (int)(m % p.W); ri.h = (int)((m / p.W) % p.H); ri.b = (int)(m / ((long long)p.W * p.H));
+  ri.row = m;
+  ri.orow = m;
+  if (p.epi.rows_per_group > 0)
+    ri.orow = (m / p.epi.rows_per_group) * (long long)p.epi.group_stride + p.epi.row_offset + (m % p.epi.rows_per_group);
+  const float* src = scratch + m * p.Npad + ch * BNW;
+  const long long stride = M * p.Npad;
+  epilogue_row<BNW, false>(p, ri, ch * BNW, [&](int c, float* v) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      float4 a = *reinterpret_cast<const float4*>(src + c + j);
+      for (int s = 1; s < ksplit; ++s) {
+        const float4 b = *reinterpret_cast<const float4*>(src + s * stride + c + j);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+    }
+  }, [](float*) {});
+}
+
+// B200_IMAGEN_GEMM_SPLITK=1: few-row, long-K GEMMs (the 8x8 levels: 64 tiles of 128 x 256 on 148 SMs) run as 2 K-splits of
+// 128 x 256 tiles + a finishing kernel instead of 128 x 128 tiles (N=128 MMAs issue at 0.63 of the N=256 rate)
+bool splitk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_IMAGEN_GEMM_SPLITK");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  return on;
+}
+int splitk_factor(long long ntiles, int Npad, int total_chunks) {
+  if (!splitk_enabled() || Npad % 256 != 0) return 1;
+  const long long t256 = ntiles * (Npad / 256);
+  return (t256 * 2 <= sm_count() && total_chunks >= 32) ? 2 : 1;   // always 2: the summation order must not depend on the batch size
+}
+
 // ------------------------------------------------------------------------------------------ host side
 
 int next_pow2(int v) {
@@ -928,7 +983,7 @@ int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorM
     B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const long long total = (long long)ntiles * (p.Npad / BN);
+  const long long total = (long long)ntiles * (p.Npad / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
   conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
   B200_LAUNCH_OK();
@@ -1010,6 +1065,15 @@ extern "C" int b200_conv_gemm_npad(int N) {
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   return (N + 127) / 128 * 128;
+}
+
+extern "C" int b200_conv_gemm_splitk(int B, int H, int W, int N, int Ktot) {
+  if (B <= 0 || H <= 0 || W <= 0 || N <= 0 || Ktot <= 0) return 1;
+  const int bw = W >= 128 ? 128 : next_pow2(W);
+  const int bh = next_pow2(H) < 128 / bw ? next_pow2(H) : 128 / bw;
+  const int bb = 128 / (bw * bh);
+  const long long ntiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((B + bb - 1) / bb);
+  return splitk_factor(ntiles, b200_conv_gemm_npad(N), Ktot / BK);
 }
 
 extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* segs, int nseg, int B, int H, int W,
@@ -1112,6 +1176,9 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
     const double c128 = (double)((t128 + sms - 1) / sms) * (128.0 / 878.0), c256 = (double)((t256 + sms - 1) / sms) * (256.0 / 1398.0);
     BN = c256 <= c128 ? 256 : 128;
   } else BN = 128;
+  p.ksplit = 1;
+  const int ks = (!pair && f32_scratch != nullptr) ? splitk_factor(ntiles, p.Npad, total) : 1;   // caller-provided partial-tile workspace
+  if (ks > 1) BN = 256;
   const int boxN = pair ? BN / 2 : BN;
   CUtensorMap maps[B200_MAX_SRC];
   memset(maps, 0, sizeof(maps));
@@ -1158,6 +1225,24 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
       B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(out) failed with %d (N=%d ldc=%d W=%d H=%d B=%d)", (int)r, N, e.ldc, W, H, B);
       p.tma_store = 1;
     }
+  }
+  if (ks > 1) {
+    // main kernel: raw fp32 partial tiles [ks][M][Npad] into the workspace; then the finishing kernel applies the real epilogue
+    GemmParams ps = p;
+    ps.ksplit = ks;
+    ps.N = p.Npad;
+    ps.tma_store = 0;
+    memset(&ps.epi, 0, sizeof(ps.epi));
+    ps.epi.out = f32_scratch;
+    ps.epi.out_mode = B200_OUT_F32;
+    ps.epi.ldc = p.Npad;
+    ps.epi.out_scale = 1.f;
+    const int rc = launch_tc2<256, 4, false, 8>(maps, mapB, mapO, ps, ntiles, st);
+    if (rc != B200_OK) return rc;
+    const long long t2 = (long long)B * H * W * (p.Npad / 64);
+    conv_gemm_splitk_epilogue_kernel<64><<<(unsigned)ceil_div64(t2, 128), 128, 0, st>>>(p, reinterpret_cast<const float*>(f32_scratch), ks);
+    B200_LAUNCH_OK();
+    return B200_OK;
   }
   if (pair) return BN == 256 ? launch_pair<256, 6>(maps, mapB, mapO, p, ntiles, st) : launch_pair<128, 8>(maps, mapB, mapO, p, ntiles, st);
   switch (BN) {

@@ -105,7 +105,7 @@ class UnetPlan:
         self._ops.append((getattr(self.lib, name), args, name))
 
     def _scratch_ptr(self, nfloats):
-        if self.impl != _lib.IMPL_SIMT_CHECKER:
+        if nfloats <= 0:
             return None
         if self._scratch is None or self._scratch.numel() < nfloats:
             self._scratch = torch.empty(int(nfloats), dtype=torch.float32, device=self.device)
@@ -119,13 +119,21 @@ class UnetPlan:
 
     def _gemm(self, srcs, segs, grid, wpacked, N, out, *, bias=None, residual=None, out2=None, l2_scale=None, ldc=None, **epi):
         gB, gH, gW = grid
+        M, npad = gB * gH * gW, _lib.npad(N)
+        if self.impl == _lib.IMPL_SIMT_CHECKER:
+            nscratch, ksplit = M * npad, 1
+        else:   # split-K workspace when the library would split this shape (few row tiles, long K: the 8x8 levels)
+            ktot = sum(-(-srcs[g[0]].C // 64) * 64 for g in segs)
+            ksplit = self.lib.b200_conv_gemm_splitk(gB, gH, gW, N, ktot)
+            nscratch = ksplit * M * npad if ksplit > 1 else 0
         call = ops.GemmCall(
             [(s.ptr, s.C, s.ld) for s in srcs], segs, grid, wpacked, N, out if isinstance(out, int) else out.data_ptr(),
             bias=ops.padded_bias(bias, N, self.device) if bias is not None else None,
             residual=residual.ptr if residual is not None else None, ldr=residual.ld if residual is not None else 0,
             out2_ptr=(out2 if isinstance(out2, int) else out2.data_ptr()) if out2 is not None else None,
             l2_scale=l2_scale, ldc=ldc if ldc is not None else 0, impl=self.impl,
-            scratch_ptr=self._scratch_ptr(gB * gH * gW * _lib.npad(N)), **epi)
+            scratch_ptr=self._scratch_ptr(nscratch), **epi)
+        call.desc['ksplit'] = ksplit
         self._keep.append(call)
         self._ops.append((call.lib.b200_conv_gemm, call.args, 'b200_conv_gemm'))
 
@@ -435,7 +443,8 @@ class UnetPlan:
             ops.append((self.lib.b200_update_time_rows, (jb.data_ptr(), len(self._jobs), self.slots.data_ptr(), R, max_elems), 'b200_update_time_rows'))
         self._ops = ops + body
         # our kernel launches per U-Net evaluation (b200_gca_gate = logits + pool + combine + 2 MLP kernels)
-        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4
+        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4 + \
+            sum(1 for c in self._keep if getattr(c, 'desc', {}).get('ksplit', 1) > 1)      # + split-K finishing kernels (GemmCall.desc)
 
     # ------------------------------------------------------------------ execution
     def describe_gemms(self):

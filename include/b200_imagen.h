@@ -112,12 +112,16 @@ typedef struct {
  * b200_conv_gemm_npad() tells the packer the N padding used for a given N. */
 int b200_conv_gemm_npad(int N);
 
+/* K-split factor the library will use for this shape WHEN a workspace is passed (1 = none): the caller then provides
+ * f32_scratch of >= factor * B*H*W * b200_conv_gemm_npad(N) floats to b200_conv_gemm (impl 0).  Ktot = sum over segments of the
+ * channel count rounded up to 64.  Without a workspace the GEMM runs unsplit. */
+int b200_conv_gemm_splitk(int B, int H, int W, int N, int Ktot);
 int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* segs, int nseg,
                    int B, int H, int W,              /* pixel grid of the OUTPUT rows: M = B*H*W */
                    const void* w_packed, int N,
                    const b200_epilogue* epi,
                    int impl,                         /* 0 = tcgen05 (product); 1 = SIMT checker used by tests */
-                   void* f32_scratch,                /* impl 1 only: >= M*Npad floats */
+                   void* f32_scratch,                /* impl 1: >= M*Npad floats; impl 0: optional split-K workspace (b200_conv_gemm_splitk) */
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ def assert_close(got, ref, rtol, atol, what=''):
 # ------------------------------------------------------------------------------------------------ conv / linear
 
 def run_conv(srcs, Wt, bias, impl, *, act=0, residual=None, out_mode=_lib.OUT_BF16, ps_C=0, dup=False, l2_cols=0, l2_scale=None,
-             split_col=0, remap=None):
+             split_col=0, remap=None, splitk=False):
     """srcs: list of [B,H,W,C] bf16; Wt [N, sumC, k, k] fp32."""
     B, H, W = srcs[0].shape[:3]
     N = Wt.shape[0]
@@ -58,6 +58,9 @@ def run_conv(srcs, Wt, bias, impl, *, act=0, residual=None, out_mode=_lib.OUT_BF
         ldc = N
     out2 = torch.zeros(out.shape[0], N - split_col, dtype=BF16, device=DEV) if split_col else None
     scratch = torch.empty(M * _lib.npad(N), dtype=torch.float32, device=DEV) if impl == 1 else None
+    if impl == 0 and splitk:
+        ks = _lib.load().b200_conv_gemm_splitk(B, H, W, N, sum(-(-srcs[g[0]].shape[-1] // 64) * 64 for g in segs))
+        scratch = torch.empty(ks * M * _lib.npad(N), dtype=torch.float32, device=DEV) if ks > 1 else None
     kw = {}
     if remap is not None:
         kw = dict(rows_per_group=remap[0], group_stride=remap[1], row_offset=remap[2])
@@ -108,6 +111,21 @@ def test_conv_gemm_matches_conv2d(name, impl):
     ref = ref_conv(srcs, Wt, bias).reshape(-1, c['N'])
     # bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise
     assert_close(out, ref, rtol=8e-3, atol=8e-3, what=name)
+
+
+@pytest.mark.parametrize('shape', [(8, 8, 8, [512], 512, 3), (4, 8, 8, [256, 128], 256, 3), (2, 1, 100, [2048], 512, 1)])
+def test_conv_gemm_with_split_k_workspace(shape):
+    """Few row tiles x long K (the 8x8 levels): with a workspace the library may split K over two CTAs per 128 x 256 tile and finish
+    with a summing epilogue kernel (B200_IMAGEN_GEMM_SPLITK=1; otherwise this runs the unsplit path).  Same result either way."""
+    B, H, W, Cs, N, k = shape
+    srcs = [rnd(B, H, W, cs, seed=i).to(BF16) for i, cs in enumerate(Cs)]
+    K = sum(Cs) * k * k
+    Wt = rnd(N, sum(Cs), k, k, scale=1 / math.sqrt(K), seed=7)
+    bias = rnd(N, scale=0.1, seed=9)
+    res = rnd(B * H * W, N, seed=5).to(BF16)
+    out, _ = run_conv(srcs, Wt, bias, _lib.IMPL_TCGEN05, act=_lib.ACT_SILU, residual=res, splitk=True)
+    ref = ref_conv(srcs, Wt, bias, act=_lib.ACT_SILU, residual=res.view(B, H, W, N)).reshape(-1, N)
+    assert_close(out, ref, rtol=8e-3, atol=8e-3)
 
 
 @pytest.mark.parametrize('impl', [_lib.IMPL_TCGEN05, _lib.IMPL_SIMT_CHECKER], ids=['tcgen05', 'simt'])
