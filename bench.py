@@ -95,6 +95,45 @@ def build_model(dim, timesteps, device):
     return b2.Imagen(unet, image_sizes=64, timesteps=timesteps).to(device)
 
 
+def build_workload(args, device):
+    """(sampler, sample kwargs, images per call, description) of BASELINE.json configs[args.config]."""
+    import imagen_pytorch_b200 as b2
+
+    def rand_final(u):
+        with torch.no_grad():
+            u.final_conv.weight.normal_(0, 0.02)
+            u.final_conv.bias.normal_(0, 0.02)
+        return u
+
+    torch.manual_seed(0)
+    c = args.config
+    if c == 1:
+        return build_model(args.dim, args.timesteps, device), dict(cond_scale=3.), args.bs, None
+    if c == 2:       # configs[2]: ElucidatedImagen base Unet dim=128 64x64, 64 sampler steps, bs=64 (CUDA-graph t-loop: 63 Heun steps + last)
+        el = b2.ElucidatedImagen(rand_final(b2.Unet(dim=args.dim)), image_sizes=64, num_sample_steps=args.sample_steps).to(device)
+        return el, dict(cond_scale=args.cond_scale), args.bs, \
+            f'BASELINE.json configs[2]: ElucidatedImagen base Unet dim={args.dim} 64x64, {args.sample_steps} sampler steps ({2 * args.sample_steps - 1} U-Net evaluations), ' \
+            f'bs={args.bs}/GPU, cond_scale={args.cond_scale}'
+    if c == 3:       # configs[3]: two-stage cascade 64 -> 256, SR-Unet dim=128 (SRUnet256), bs=8, 100 DDPM steps each
+        im = b2.Imagen((rand_final(b2.Unet(dim=args.dim)), rand_final(b2.SRUnet256(lowres_cond=True))), image_sizes=(64, 256),
+                       timesteps=args.timesteps).to(device)
+        return im, dict(cond_scale=args.cond_scale), args.bs, \
+            f'BASELINE.json configs[3]: cascade base Unet dim={args.dim} @64 -> SRUnet256 (dim 128, lowres_cond) @256, bs={args.bs}/GPU, ' \
+            f'{args.timesteps} DDPM steps each, cond_scale={args.cond_scale}'
+    if c == 4:       # configs[4]: the per-GPU shard of base Unet dim=192 64x64, 1000 steps, global bs 512 over 8 GPUs
+        return build_model(args.dim, args.timesteps, device), dict(cond_scale=3.), args.bs, \
+            f'BASELINE.json configs[4] per-GPU shard: base Unet dim={args.dim} 64x64, bs={args.bs}/GPU (global 512 over 8 GPUs), {args.timesteps} DDPM steps, cond_scale=3.0'
+    raise ValueError(f'unknown --config {c}')
+
+
+def gpu_eager_step_time(dim, bs, device, steps):
+    """The reference's eager fp32 PyTorch ops (oracle port, torch CUDA kernels: cuDNN TF32 convs, cuBLAS, materialised N x M attention)
+    on THIS GPU in THIS process: `steps` denoising steps at the full batch -> seconds per denoising step (the denominator of the
+    north star's ">= 15x PyTorch-eager on 1xB200")."""
+    cpu_reference_step(dim, bs, device=str(device), steps=2)            # warm-up (cuDNN autotune, allocator)
+    return cpu_reference_step(dim, bs, device=str(device), steps=steps)
+
+
 def time_attention_kernel(bs_rows, device, iters=10, max_logit=8 * 1.4426950408889634 * 1.02):
     """The dominant kernel alone, at the workload's shape: one 64x64 multi-query self-attention block, R = 2*bs rows."""
     from imagen_pytorch_b200 import _lib
@@ -217,7 +256,11 @@ def run_reference(args):
     }))
 
 
-def workload_config(args):
+def workload_config(args, desc=None):
+    if desc is not None:
+        return {'workload': desc + f', random text_embeds ({args.bs},256,768)', 'global_batch': args.bs * args.gpus,
+                'parallelism': f'dp{args.gpus} (independent sample shards, one all-gather of finished images)',
+                'l2': 'no explicit flush: the per-step activation working set (GBs) exceeds the 126 MB L2'}
     return {'workload': f'BASELINE.json configs[1]: base Unet dim={args.dim} 64x64, bs={args.bs}/GPU, {args.timesteps} DDPM steps, cond_scale=3.0 '
                         f'(classifier-free guidance: {2 * args.bs} U-Net rows/step), random text_embeds ({args.bs},256,768)',
             'global_batch': args.bs * args.gpus, 'parallelism': f'dp{args.gpus} (independent sample shards, one all-gather of finished images)',
@@ -230,12 +273,20 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--bs', type=int, default=16)
-    ap.add_argument('--dim', type=int, default=128)
-    ap.add_argument('--timesteps', type=int, default=1000)
+    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4], help='index into BASELINE.json configs (1 = the headline metric)')
+    ap.add_argument('--bs', type=int, default=None)
+    ap.add_argument('--dim', type=int, default=None)
+    ap.add_argument('--timesteps', type=int, default=None)
+    ap.add_argument('--sample-steps', type=int, default=64, help='config 2: ElucidatedImagen num_sample_steps')
+    ap.add_argument('--cond-scale', type=float, default=3.0, help='configs 2 and 3')
+    ap.add_argument('--eager-steps', type=int, default=20, help='denoising steps of the in-process eager-PyTorch-on-GPU baseline (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager-gpu', action='store_true', help='with --impl reference: run the oracle port with torch CUDA ops (informational)')
     args = ap.parse_args()
+    defaults = {1: (16, 128, 1000), 2: (64, 128, None), 3: (8, 128, 100), 4: (64, 192, 1000)}[args.config]
+    args.bs = args.bs if args.bs is not None else defaults[0]
+    args.dim = args.dim if args.dim is not None else defaults[1]
+    args.timesteps = args.timesteps if args.timesteps is not None else (defaults[2] or 1000)
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -251,21 +302,22 @@ def main():
     assert args.warmup >= 3, 'timing hygiene: at least 3 warm-up steps'
 
     from imagen_pytorch_b200.dist import all_gather_images
-    imagen = build_model(args.dim, args.timesteps, device)
+    imagen, skw, bs_call, desc = build_workload(args, device)
+    out_px = imagen.image_sizes[-1]
     torch.manual_seed(1234 + rank)
     te_host = torch.randn(args.bs, 256, 768).pin_memory()
     te_dev = te_host.to(device)
-    out_host = torch.empty(args.bs, 3, 64, 64).pin_memory()
+    out_host = torch.empty(args.bs, 3, out_px, out_px).pin_memory()
 
     def step_resident():
-        img = imagen.sample(text_embeds=te_dev, cond_scale=3., use_tqdm=False)
+        img = imagen.sample(text_embeds=te_dev, use_tqdm=False, **skw)
         if world > 1:
             img = all_gather_images(img, [args.bs] * world)
         return img
 
     def step_e2e():
         te = te_host.to(device, non_blocking=True)          # H2D of this step's inputs from pinned memory
-        img = imagen.sample(text_embeds=te, cond_scale=3., use_tqdm=False)
+        img = imagen.sample(text_embeds=te, use_tqdm=False, **skw)
         if world > 1:
             img = all_gather_images(img, [args.bs] * world)
         out_host.copy_(img[rank * args.bs:(rank + 1) * args.bs] if world > 1 else img, non_blocking=True)   # D2H of the result
@@ -283,19 +335,26 @@ def main():
         e1.record()
         torch.cuda.synchronize(device)
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        per_rank = [ms.item()]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            allms = torch.empty(world, device=device)
+            dist.all_gather_into_tensor(allms, ms)              # every rank's own device time: a slow GPU shows up by index
+            per_rank = allms.tolist()
             dist.barrier()
-        return ms.item()
+        return max(per_rank), per_rank                         # the job's time is the slowest rank's
 
     for _ in range(args.warmup):
         step_resident()
     with ClockSampler(local) as clk:
-        ms = timed(step_resident, args.steps)
+        ms, ms_ranks = timed(step_resident, args.steps)
     clocks = clk.summary()
     launches = imagen.last_launch_count * args.steps
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, ms_e2e_ranks = timed(step_e2e, args.steps)
+    rank_clocks = [clocks]
+    if world > 1:                                               # per-rank clocks under load next to the per-rank times
+        rank_clocks = [None] * world
+        dist.all_gather_object(rank_clocks, clocks)
 
     images = args.bs * world * args.steps
     value = images / (ms / 1e3)
@@ -304,10 +363,16 @@ def main():
     line = {
         'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
-        'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks, 'gpu_launches': launches,
+        'data': 'synthetic', 'config': workload_config(args, desc), 'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': te_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4},
+        'per_rank': {'ms_per_step': [m / args.steps for m in ms_ranks], 'ms_per_step_min': min(ms_ranks) / args.steps,
+                     'ms_per_step_median': statistics.median(ms_ranks) / args.steps, 'ms_per_step_max': max(ms_ranks) / args.steps,
+                     'e2e_ms_per_step': [m / args.steps for m in ms_e2e_ranks],
+                     'sm_mhz': [c.get('sm_mhz') for c in rank_clocks], 'reasons': [c.get('reasons') for c in rank_clocks]},
     }
-    if rank == 0:
+    if rank == 0 and args.config != 1:
+        print(json.dumps(line))
+    if rank == 0 and args.config == 1:
         R = 2 * args.bs
         att_ms = time_attention_kernel(R, device)
         att_tflops = ATTN_L0_GFLOP_PER_SAMPLE * R / 1e3 / (att_ms / 1e3)
@@ -329,6 +394,16 @@ def main():
         if step_tflop:
             ach = step_tflop / (ms / args.steps / 1e3)
             line['whole_step'] = {'algorithmic_tflop_per_step': step_tflop, 'achieved_tflops': ach, 'frac_of_sustained_bf16': ach / pk['tensor_sustained']}
+        if args.eager_steps > 0:
+            # the north star's ">= 15x the reference PyTorch-eager images/sec on 1xB200": same GPU, same process, same batch
+            with ClockSampler(local) as eclk:
+                dt = gpu_eager_step_time(args.dim, args.bs, device, args.eager_steps)
+            eager = args.bs / (dt * args.timesteps)
+            line['gpu_eager_baseline'] = {'value': eager, 'unit': 'images/s', 'ms_per_denoising_step': dt * 1e3, 'denoising_steps_timed': args.eager_steps,
+                                          'batch': args.bs, 'dtype': 'f32 (TF32 convolutions, cuDNN / cuBLAS / ATen eager kernels)', 'clocks': eclk.summary(),
+                                          'speedup_value': value / world / eager, 'speedup_e2e': e2e_value / world / eager,
+                                          'what': f'oracle port of the reference forward + DDPM step executed with torch CUDA ops on this GPU: {args.eager_steps} denoising steps '
+                                                  f'(cond + null pass, cond_scale 3.0) at bs={args.bs}, extrapolated x{args.timesteps}; informational baseline, not the product path'}
         if not args.no_cpu_baseline:
             cores = usable_cores()
             torch.set_num_threads(cores)

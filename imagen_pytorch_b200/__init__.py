@@ -6,7 +6,7 @@ Public names mirror the reference package (imagen_pytorch/__init__.py) for the p
 from .unet import Unet, NullUnet, BaseUnet64, SRUnet256, SRUnet1024, UnetPlan
 from .imagen import Imagen, GaussianDiffusionContinuousTimes
 from .elucidated import ElucidatedImagen
-from .dist import sample_sharded
+from .dist import sample_sharded, sample_in_chunks
 from ._lib import B200Error, LIB_PATH
 
 __version__ = '0.1.0'

@@ -40,15 +40,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
 // byte offset of 16-byte chunk `c` of row `r` in a [rows][64] bf16 tile with XOR swizzle
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-static inline int sm_count_attn() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static inline int sm_count_attn() { return b200_sm_count(); }
 
 struct AttnParams {
   const __nv_bfloat16* q;
@@ -406,11 +398,7 @@ extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs
     static const bool on = [] { const char* e = getenv("B200_IMAGEN_XATTN_FEWKEYS"); return e == nullptr || atoi(e) != 0; }();
     if (on) {
       constexpr int xsmem = 2 * ATT_BN * 128 + XA_QBUF * ATT_BM * 128;
-      static bool xconfigured = false;
-      if (!xconfigured) {
-        B200_CUDA_OK(cudaFuncSetAttribute(cross_attn_fewkeys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, xsmem));
-        xconfigured = true;
-      }
+      B200_SMEM_OPT_IN(cross_attn_fewkeys_kernel, xsmem);
       // contiguous tile ranges per CTA; one wave of CTAs (2 resident per SM) when the problem allows
       const int ntiles = (rows + ATT_BM - 1) / ATT_BM;
       const long long pairs = (long long)B * n_heads;
@@ -425,11 +413,7 @@ extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs
     }
   }
   constexpr int smem = ATT_BM * 128 + 4 * ATT_BN * 128;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  B200_SMEM_OPT_IN(flash_attn_kernel, smem);
   dim3 grid((rows + ATT_BM - 1) / ATT_BM, n_heads, B);
   flash_attn_kernel<<<grid, ATT_THREADS, smem, st>>>(p);
   B200_LAUNCH_OK();

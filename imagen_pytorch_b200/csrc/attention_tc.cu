@@ -526,6 +526,236 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// "P in tensor memory" variant of the ping-pong kernel.  The softmax warps write the bf16 probabilities back to TMEM with
+// tcgen05.st (two keys per 32-bit column, row = lane) and the O += P V MMA takes its A operand from TMEM (tcgen05.mma with
+// [a_tmem]): no shared-memory P tile, no generic->async proxy fence per chunk, no bank conflicts, and the P V MMAs read
+// only V (2 KB per K=16 step) from shared memory.  The 64 KB of shared memory the P tiles used become a deeper K/V ring.
+// The last key tile's second half is skipped when it holds no valid key (4135 keys = 32 tiles + 39 keys).
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)  (P: 64 keys per 32 columns).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PT_STAGES = 5;
+constexpr int PT_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 256 + 2048;   // + barriers + row-sum exchange
+
+template <int POLY>
+__device__ __forceinline__ bool pt_use_poly(int idx) { return POLY > 0 && (idx % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1; }
+
+template <int POLY, int SUB>   // POLY: every POLY-th exponential on the FMA pipe (0 = all MUFU); SUB: softmax warps per lane quarter per group
+__global__ void __launch_bounds__(128 + 256 * SUB, 1)
+flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [2] query tiles
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [PT_STAGES] {K, V}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + PT_STAGES * FA_KV_BYTES);
+  uint64_t* q_full = bars;                              // [1]
+  uint64_t* kv_full = bars + 1;                         // [PT_STAGES]
+  uint64_t* kv_empty = kv_full + PT_STAGES;             // [PT_STAGES] (count 2: both groups' P V MMAs)
+  uint64_t* s_full = kv_empty + PT_STAGES;              // [group]
+  uint64_t* s_empty = s_full + 2;                       // [group]
+  uint64_t* p_full = s_empty + 2;                       // [group][half]
+  uint64_t* p_empty = p_full + 4;                       // [group][half]
+  uint64_t* o_full = p_empty + 4;                       // [group]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* sL = reinterpret_cast<float*>(bars + 32);      // [group][sub][128] partial row sums
+  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 1 <= 32, "barrier block is 256 bytes");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * (2 * FA_BM);
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
+  const bool dead1 = (ntiles - 1) * FA_BN + 64 >= p.n_keys;   // the last tile's second 64-key half holds no valid key
+  constexpr uint32_t TM_O = 256, TM_P = 384;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 128 * SUB);
+      mbar_init(&o_full[g], 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: both query tiles, then the K/V ring
+      mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
+      for (int g = 0; g < 2; ++g) {
+        if (p.q_heads_first) tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, h, row0 + g * FA_BM, b);
+        else tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, row0 + g * FA_BM, h, b);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % PT_STAGES;
+        const uint32_t n = (uint32_t)(j / PT_STAGES);
+        mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
+        uint8_t* dst = sKV + st * FA_KV_BYTES;
+        if (p.kv_heads_first) {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+        } else {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      // ---------------- MMA issuer of group g
+      const int g = warp - 1;
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+      auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
+        const int st = j % PT_STAGES;
+        mbar_wait(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1));
+        mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
+        tc_fence_after();
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        const int st = j % PT_STAGES;
+        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+        for (int hf = 0; hf < 2; ++hf) {        // the first 64 keys are multiplied while the second 64 are exponentiated
+          if (hf == 1 && dead1 && j == ntiles - 1) break;
+          const int pb = 2 * g + hf;
+          mbar_wait(&p_full[pb], (uint32_t)(j & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // A: 16 keys = 8 packed columns of this half's P block; B: 16 key rows of V (MN-major, 2 KB)
+            const uint32_t a_tmem = tmem_base + TM_P + (uint32_t)(g * 64 + hf * 32 + k * 8);
+            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((hf * 4 + k) * 16 * 128), 1024, 1024);
+            umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, (j | hf | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&p_empty[pb]);
+        }
+        umma_commit(&kv_empty[st]);             // one of the two arrivals that free K_j / V_j
+      }
+      umma_commit(&o_full[g]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax / epilogue: group g, thread = (query row of that group, 64-key half if SUB == 2)
+    const int idx = warp - 4;
+    const int g = idx / (4 * SUB);
+    const int sub = (idx >> 2) % SUB;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float l = 0.f;
+    const float C = p.max_logit;
+    for (int j = 0; j < ntiles; ++j) {
+      const int key0 = j * FA_BN;
+      const bool ragged = key0 + FA_BN > p.n_keys;
+      const bool last_dead = dead1 && j == ntiles - 1;
+      if (SUB == 2 && sub == 1 && last_dead) break;     // nothing valid in this warp's half of the last tile
+      mbar_wait(&s_full[g], (uint32_t)(j & 1));
+      tc_fence_after();
+      constexpr int CH = SUB == 2 ? 32 : 64;
+#pragma unroll 1
+      for (int hh = 0; hh < 2 / SUB; ++hh) {
+        const int hf = SUB == 2 ? sub : hh;
+        if (hf == 1 && last_dead) break;
+        const int pb = 2 * g + hf;
+        const uint32_t p_col = tmem_base + lane_off + TM_P + (uint32_t)(g * 64 + hf * 32);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += CH) {
+          uint32_t sr[CH];
+#pragma unroll
+          for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
+          if (c0 + CH == 64 && (SUB == 2 || hh == 1 || last_dead)) {
+            tc_fence_before();
+            mbar_arrive(&s_empty[g]);           // this thread's share of S_g is in registers
+          }
+          if (c0 == 0) {
+            mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half of P
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int t = 0; t < CH / 32; ++t) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int e = 32 * t + i;
+              const float x0 = __uint_as_float(sr[e]) - C, x1 = __uint_as_float(sr[e + 1]) - C;
+              float p0 = pt_use_poly<POLY>(e) ? ex2_poly(x0) : ex2_approx(x0);
+              float p1 = pt_use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2_approx(x1);
+              if (ragged) {
+                if (key0 + hf * 64 + c0 + e >= p.n_keys) p0 = 0.f;
+                if (key0 + hf * 64 + c0 + e + 1 >= p.n_keys) p1 = 0.f;
+              }
+              l += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+            tmem_st16(p_col + (uint32_t)((c0 + 32 * t) >> 1), pk);
+          }
+        }
+        tmem_st_wait();                          // the stores have landed in tensor memory ...
+        tc_fence_before();                       // ... and are ordered before the issuer's MMAs through the barrier
+        mbar_arrive(&p_full[pb]);
+      }
+    }
+    // ---- O / l -> global (with SUB == 2 the two column-half threads of a row add their sums and each stores 32 channels)
+    mbar_wait(&o_full[g], 0);
+    tc_fence_after();
+    if (SUB == 2) {
+      float* sLg = sL + g * 2 * FA_BM;
+      sLg[sub * FA_BM + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");         // the 8 softmax warps of this group
+      l = sLg[r] + sLg[FA_BM + r];
+    }
+    const float inv = 1.f / l;
+    const int row = row0 + g * FA_BM + r;
+    constexpr int OC = FA_D / SUB;
+    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + sub * OC;
+    uint32_t orr[OC];
+#pragma unroll
+    for (int c = 0; c < OC; c += 32) tmem_ld32_nowait(tmem_base + lane_off + TM_O + (uint32_t)(g * FA_D + sub * OC + c), orr + c);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < OC; ++i) asm volatile("" : "+r"(orr[i]));
+    if (row < p.rows) {
+#pragma unroll
+      for (int t = 0; t < OC / 8; ++t) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + 8 * t) = u;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
 // 4-D map over [B][rows x heads][64]: dim0 = 64 head channels, dims 1/2 = (rows, heads) ordered by ascending stride
 // (heads_first: the 8 heads of a row are adjacent, as in the cross-attention q / k / v layout), dim3 = batch.
 int encode_rows_map(CUtensorMap* map, const void* base, int rows, int n_heads, int B, long long rs, long long hs, long long bs, int box_rows,
@@ -579,11 +809,7 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   }
 #define FA_LAUNCH(NW, PF, WA)                                                                                                      \
   {                                                                                                                                \
-    static bool configured = false;                                                                                                \
-    if (!configured) {                                                                                                             \
-      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_tc_kernel<NW, PF, WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));  \
-      configured = true;                                                                                                           \
-    }                                                                                                                              \
+    B200_SMEM_OPT_IN((flash_attn_tc_kernel<NW, PF, WA>), FA_SMEM);                                                                 \
     flash_attn_tc_kernel<NW, PF, WA><<<grid, 64 + 32 * NW, FA_SMEM, st>>>(mq, mk, mv, p);                                         \
   }
   switch (variant) {
@@ -598,11 +824,7 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 8: FA_LAUNCH(4, false, true); break;
 #define PP_LAUNCH(POLY, SUB)                                                                                                     \
   {                                                                                                                                \
-    static bool configured = false;                                                                                                \
-    if (!configured) {                                                                                                             \
-      B200_CUDA_OK(cudaFuncSetAttribute(flash_attn_pp_kernel<POLY, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));  \
-      configured = true;                                                                                                           \
-    }                                                                                                                              \
+    B200_SMEM_OPT_IN((flash_attn_pp_kernel<POLY, SUB>), PP_SMEM);                                                                  \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
     flash_attn_pp_kernel<POLY, SUB><<<grid2, 128 + 256 * SUB, PP_SMEM, st>>>(mq, mk, mv, p);                                      \
   }
@@ -610,6 +832,22 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
     case 12: PP_LAUNCH(0, 2); break;   // ping-pong, 16 softmax warps (column halves)
     case 13: PP_LAUNCH(4, 2); break;   // ... + 1/4 polynomial exp2
+#define PT_LAUNCH(POLY, SUB)                                                                                                     \
+  {                                                                                                                                \
+    B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB>), PT_SMEM);                                                                  \
+    dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
+    flash_attn_pt_kernel<POLY, SUB><<<grid2, 128 + 256 * SUB, PT_SMEM, st>>>(mq, mk, mv, p);                                      \
+  }
+    case 20: PT_LAUNCH(0, 2); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
+    case 21: PT_LAUNCH(8, 2); break;   // ... + 1/8 of the exponentials on the FMA pipe
+    case 22: PT_LAUNCH(5, 2); break;   // ... + 1/5
+    case 23: PT_LAUNCH(4, 2); break;   // ... + 1/4
+    case 24: PT_LAUNCH(3, 2); break;   // ... + 1/3
+    case 25: PT_LAUNCH(2, 2); break;   // ... + 1/2
+    case 26: PT_LAUNCH(0, 1); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
+    case 27: PT_LAUNCH(4, 1); break;
+    case 28: PT_LAUNCH(3, 1); break;
+#undef PT_LAUNCH
     default: PP_LAUNCH(0, 1); break;   // ping-pong: two query tiles per CTA, all exponentials on MUFU
 #undef PP_LAUNCH
   }

@@ -27,6 +27,28 @@ void b200_set_error(const char* fmt, ...);
   } while (0)
 #define B200_LAUNCH_OK() B200_CUDA_OK(cudaGetLastError())
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE function attribute: opt in once per (kernel, device), so a process
+// that samples on cuda:0 and then on cuda:1 does not launch with the 48 KB default on the second device.
+#define B200_SMEM_OPT_IN(func, bytes)                                                                              \
+  do {                                                                                                             \
+    static unsigned long long done__[2] = {0ull, 0ull};                                                            \
+    int dev__ = 0;                                                                                                 \
+    B200_CUDA_OK(cudaGetDevice(&dev__));                                                                           \
+    if (dev__ < 0 || dev__ >= 128 || !((done__[dev__ >> 6] >> (dev__ & 63)) & 1ull)) {                             \
+      B200_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));              \
+      if (dev__ >= 0 && dev__ < 128) done__[dev__ >> 6] |= 1ull << (dev__ & 63);                                   \
+    }                                                                                                              \
+  } while (0)
+
+// SM count of the CURRENT device (cached per device)
+static inline int b200_sm_count() {
+  static int n[128] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return 148;
+  if (n[dev] == 0 && (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0)) n[dev] = 148;
+  return n[dev];
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- small device helpers

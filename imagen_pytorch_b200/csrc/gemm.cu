@@ -978,11 +978,7 @@ template <int BN, int STAGES, bool SIMPLE, int NEPI>
 int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
   constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + NEPI * EPI_STAGE_BYTES : 0) /*staging*/;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  B200_SMEM_OPT_IN((conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI>), smem);
   const long long total = (long long)ntiles * (p.Npad / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
   conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
@@ -1032,11 +1028,7 @@ template <int BN, int STAGES, bool SIMPLE>
 int launch_pair2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
   constexpr int smem = STAGES * (A_TILE_BYTES + (BN / 2) * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + 8 * EPI_STAGE_BYTES : 0) /*staging*/;
   static_assert(smem <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_gemm_tc2_kernel<BN, STAGES, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  B200_SMEM_OPT_IN((conv_gemm_tc2_kernel<BN, STAGES, SIMPLE>), smem);
   const long long total = (long long)((ntiles + 1) / 2) * (p.Npad / BN);     // 256 x BN tiles
   const int pairs = (int)(total < sm_count() / 2 ? total : sm_count() / 2);  // persistent: one CTA pair per TPC
   conv_gemm_tc2_kernel<BN, STAGES, SIMPLE><<<2 * pairs, 64 + 256, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);

@@ -282,11 +282,7 @@ extern "C" int b200_ddpm_step_sc(float* x, const float* pred, const float* noise
   B200_REQUIRE(!thresholding || (q_lo >= 0 && q_hi >= q_lo && q_hi <= q_lo + 1 && q_hi < chw), "ddpm_step: bad quantile ranks");
   Quant q{q_lo, q_hi, q_w, thresholding};
   const int smem = smp_smem(chw);
-  static bool cfg = false;   // dynamic cache + 1.2 KB static histogram exceeds the 48 KB default already at 3x64x64
-  if (!cfg) {
-    B200_CUDA_OK(cudaFuncSetAttribute(ddpm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_CACHE_FLOATS * 4));
-    cfg = true;
-  }
+  B200_SMEM_OPT_IN(ddpm_step_kernel, SMP_CACHE_FLOATS * 4);   // dynamic cache + 1.2 KB static histogram exceeds the 48 KB default already at 3x64x64
   ddpm_step_kernel<<<B, SMP_THREADS, smem, st>>>(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q, x_start_out);
   B200_LAUNCH_OK();
   return B200_OK;
@@ -308,11 +304,7 @@ extern "C" int b200_edm_phase_sc(int phase, float* x, float* x_hat, float* x1, f
   B200_REQUIRE(B > 0 && (R == B || R == 2 * B) && chw > 0, "edm_phase: bad R=%d B=%d", R, B);
   Quant q{q_lo, q_hi, q_w, thresholding};
   const int smem = phase == 0 ? 0 : smp_smem(chw);
-  static bool cfg = false;
-  if (!cfg) {
-    B200_CUDA_OK(cudaFuncSetAttribute(edm_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMP_CACHE_FLOATS * 4));
-    cfg = true;
-  }
+  B200_SMEM_OPT_IN(edm_phase_kernel, SMP_CACHE_FLOATS * 4);
   if (phase == 0) {
     // commit the step counter staged by the previous step's last phase (step_ctr[1]); step_ctr is int32[2]
     edm_commit_step_kernel<<<1, 1, 0, st>>>(step_ctr);

@@ -50,6 +50,59 @@ class Rows:
         return self.t.shape[0]
 
 
+class _Arena:
+    """Bump allocator over a few large device chunks.  zero=True: chunks come from torch.zeros (activations; padded channels and
+    prefix rows rely on it).  staged=True: every chunk has a host twin that `put` fills; `flush` uploads it with one memcpy, so
+    packing ~300 weight operands costs no kernel launches (the driver's launch trace then shows the product kernels)."""
+    ALIGN = 1024
+
+    def __init__(self, device, *, zero, chunk, staged=False):
+        self.device, self.zero, self.chunk, self.staged = device, zero, chunk, staged
+        self.chunks, self.hosts, self.off = [], [], 0
+
+    def _grow(self, nbytes):
+        size = max(min(self.chunk, (32 << 20) << (2 * len(self.chunks))), nbytes)    # 32 MB, 128 MB, 512 MB, ... up to `chunk`
+        self.chunks.append((torch.zeros if self.zero else torch.empty)(size, dtype=torch.uint8, device=self.device))
+        if self.staged:
+            self.hosts.append(torch.empty(size, dtype=torch.uint8))
+        self.off = 0
+
+    def _take(self, nbytes):
+        nbytes = max(int(nbytes), 1)
+        if not self.chunks or self.off + nbytes > self.chunks[-1].numel():
+            self._grow(nbytes)
+        o = self.off
+        self.off = (o + nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return len(self.chunks) - 1, o
+
+    def alloc(self, shape, dtype):
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        n = 1
+        for v in shape:
+            n *= v
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        c, o = self._take(nbytes)
+        return self.chunks[c][o:o + nbytes].view(dtype).view(shape)
+
+    def put(self, host: torch.Tensor):
+        assert self.staged and host.device.type == 'cpu'
+        host = host.contiguous()
+        nbytes = host.numel() * host.element_size()
+        c, o = self._take(nbytes)
+        if nbytes:
+            self.hosts[c][o:o + nbytes].copy_(host.view(-1).view(torch.uint8))
+        return self.chunks[c][o:o + max(nbytes, 0)].view(host.dtype).view(host.shape)
+
+    def flush(self):
+        for i, (d, h) in enumerate(zip(self.chunks, self.hosts)):
+            used = self.off if i == len(self.chunks) - 1 else d.numel()
+            d[:used].copy_(h[:used])
+        self.hosts = []
+
+    def nbytes(self):
+        return sum(c.numel() for c in self.chunks)
+
+
 class UnetPlan:
     """Launch plan of one U-Net for a fixed (rows R, images B, H, W, schedule slots S)."""
 
@@ -64,8 +117,15 @@ class UnetPlan:
         div = 2 ** (nlev if a.memory_efficient else nlev - 1)
         if H % div or W % div:
             raise ValueError(f'image size {H}x{W} must be divisible by {div} for this U-Net')
+        # device-side fp32 views of the parameters (no copy when the module already lives on `device`): read by prepare()
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in unet.state_dict().items()}
-        self._keep = []
+        # host copies for weight packing: the packed bf16 / fp32 operands are assembled on the host into a few staging chunks and
+        # reach the device with one memcpy per chunk, so building a plan launches (almost) no kernels of its own
+        self.sdc = {k: v.detach().to(device='cpu', dtype=torch.float32) for k, v in unet.state_dict().items()}
+        self.fingerprint = unet._fingerprint()
+        self._keep, self._post = [], []
+        self._act = _Arena(device, zero=True, chunk=1 << 30)      # activations / state: zero-filled chunks (one fill kernel per GiB)
+        self._wts = _Arena(device, zero=False, chunk=1 << 28, staged=True)
         self._ops = []
         self._jobs = []
         self.cross_layers, self.self_layers = [], []
@@ -89,17 +149,14 @@ class UnetPlan:
 
     # ------------------------------------------------------------------ small helpers
     def _zeros(self, shape, dtype=BF16):
-        t = torch.zeros(shape, dtype=dtype, device=self.device)
-        self._keep.append(t)
-        return t
+        return self._act.alloc(shape, dtype)
 
     def _new(self, rows, C, H=1, W=1):
         return Rows(self._zeros((rows, C)), C, H, W)
 
     def _f32(self, t):
-        t = t.to(device=self.device, dtype=torch.float32).contiguous()
-        self._keep.append(t)
-        return t
+        """host fp32 tensor -> device copy (through the staged weight arena)."""
+        return self._wts.put(t.to(dtype=torch.float32).contiguous())
 
     def _add(self, name, *args):
         self._ops.append((getattr(self.lib, name), args, name))
@@ -112,10 +169,12 @@ class UnetPlan:
             self._keep.append(self._scratch)
         return self._scratch.data_ptr()
 
+    def _row_fill(self, dst, row):
+        """dst[r, :] = row (host fp32 -> bf16) for every r, applied after the staged weights have reached the device."""
+        self._post.append((dst, self._wts.put(row.to(BF16).contiguous())))
+
     def _pack(self, mats, N):
-        out = ops.pack_weight(mats, N, self.device)
-        self._keep.append(out)
-        return out
+        return self._wts.put(ops.pack_weight(mats, N, 'cpu'))
 
     def _gemm(self, srcs, segs, grid, wpacked, N, out, *, bias=None, residual=None, out2=None, l2_scale=None, ldc=None, **epi):
         gB, gH, gW = grid
@@ -128,7 +187,7 @@ class UnetPlan:
             nscratch = ksplit * M * npad if ksplit > 1 else 0
         call = ops.GemmCall(
             [(s.ptr, s.C, s.ld) for s in srcs], segs, grid, wpacked, N, out if isinstance(out, int) else out.data_ptr(),
-            bias=ops.padded_bias(bias, N, self.device) if bias is not None else None,
+            bias=self._wts.put(ops.padded_bias(bias, N, 'cpu')) if bias is not None else None,
             residual=residual.ptr if residual is not None else None, ldr=residual.ld if residual is not None else 0,
             out2_ptr=(out2 if isinstance(out2, int) else out2.data_ptr()) if out2 is not None else None,
             l2_scale=l2_scale, ldc=ldc if ldc is not None else 0, impl=self.impl,
@@ -165,7 +224,7 @@ class UnetPlan:
     # ------------------------------------------------------------------ blocks
     def _resnet(self, p, srcs, dout, *, cross_heads=None, gca=False):
         """ResnetBlock.forward (imagen_pytorch.py:735-757)."""
-        a, sd, R = self.arch, self.sd, self.R
+        a, sd, R = self.arch, self.sdc, self.R
         Hc, Wc = srcs[0].H, srcs[0].W
         n = Hc * Wc
         M = R * n
@@ -230,7 +289,7 @@ class UnetPlan:
 
     def _gca(self, p, h: Rows):
         """GlobalContext (imagen_pytorch.py:945-970) -> gate [R, C] fp32."""
-        sd, R = self.sd, self.R
+        sd, R = self.sdc, self.R
         n, Cc = h.H * h.W, h.C
         hid = sd[p + '.net.0.weight'].shape[0]
         nchunk = self.lib.b200_gca_nchunk(n)
@@ -250,11 +309,11 @@ class UnetPlan:
         The attention ABI takes the tcgen05 fixed-bound path when this is <= 40, else the online-softmax kernel."""
         if os.environ.get('B200_IMAGEN_ATTN', 'tc') == 'mma':
             return 0.0
-        return float((self.sd[p + '.q_scale'].abs() * self.sd[p + '.k_scale'].abs()).max().item()) * 8.0 * LOG2E * 1.02
+        return float((self.sdc[p + '.q_scale'].abs() * self.sdc[p + '.k_scale'].abs()).max().item()) * 8.0 * LOG2E * 1.02
 
     def _cross_attention(self, p, h: Rows, heads):
         """CrossAttention.forward + residual (imagen_pytorch.py:793-834, :749)."""
-        sd, R = self.sd, self.R
+        sd, R = self.sdc, self.R
         n, M, Cc = h.H * h.W, h.rows, h.C
         inner = heads * 64
         hn = self._layernorm(h, sd[p + '.norm.g'])
@@ -268,8 +327,8 @@ class UnetPlan:
             self._jobs.append(TimeRowJob(tb.data_ptr(), dst.data_ptr(), nk * inner, self.ntt, inner))
         # static null key/value: last row, same for every head (:805-808)
         nkv = sd[p + '.null_kv']
-        Kc[:, nk - 1, :] = (F.normalize(nkv[0], dim=-1) * sd[p + '.k_scale']).repeat(heads).to(BF16)
-        Vc[:, nk - 1, :] = nkv[1].repeat(heads).to(BF16)
+        self._row_fill(Kc[:, nk - 1, :], (F.normalize(nkv[0], dim=-1) * sd[p + '.k_scale']).repeat(heads))
+        self._row_fill(Vc[:, nk - 1, :], nkv[1].repeat(heads))
         o = self._new(M, inner, h.H, h.W)
         self._add('b200_attention', q.ptr, o.ptr, n * inner, 64, inner, n, Kc.data_ptr(), Vc.data_ptr(), nk * inner, 64, inner, nk, R, heads,
                   self._logit_bound(p))
@@ -278,7 +337,7 @@ class UnetPlan:
 
     def _transformer(self, p, x: Rows, depth, has_ctx):
         """TransformerBlock.forward (imagen_pytorch.py:1012-1022): multi-query self-attention + feed-forward."""
-        a, sd, R = self.arch, self.sd, self.R
+        a, sd, R = self.arch, self.sdc, self.R
         n, M, Cc = x.H * x.W, x.rows, x.C
         heads, inner = a.heads, a.inner
         for l in range(depth):
@@ -294,8 +353,8 @@ class UnetPlan:
             self._gemm([xn], [(0, 0, 0)], (1, 1, M), self._pack([sd[q_ + '.to_kv.weight']], 128), 128, Kb, ldc=64, out2=Vb, ldc2=64,
                        split_col=64, rows_per_group=n, group_stride=Mtot, row_offset=npre, l2_cols=64, l2_scale=ks)
             nkv = sd[q_ + '.null_kv']
-            Kb[:, npre - 1, :] = (F.normalize(nkv[0], dim=-1) * sd[q_ + '.k_scale']).to(BF16)
-            Vb[:, npre - 1, :] = nkv[1].to(BF16)
+            self._row_fill(Kb[:, npre - 1, :], F.normalize(nkv[0], dim=-1) * sd[q_ + '.k_scale'])
+            self._row_fill(Vb[:, npre - 1, :], nkv[1])
             layer = dict(p=q_, K=Kb, V=Vb, has_ctx=has_ctx, Mtot=Mtot)
             if has_ctx:
                 Kt, Vt = self._zeros((self.S, self.ntt, 64)), self._zeros((self.S, self.ntt, 64))
@@ -318,7 +377,7 @@ class UnetPlan:
 
     def _downsample(self, p, x: Rows, dout):
         """Downsample = pixel-unshuffle + 1x1 conv (imagen_pytorch.py:633-640)."""
-        sd, R = self.sd, self.R
+        sd, R = self.sdc, self.R
         H2, W2 = x.H // 2, x.W // 2
         xs = self._new(R * H2 * W2, 4 * x.C, H2, W2)
         self._add('b200_pixel_unshuffle', x.ptr, x.ld, R, x.H, x.W, x.C, xs.ptr)
@@ -328,7 +387,7 @@ class UnetPlan:
 
     def _upsample(self, p, x: Rows, dout):
         """PixelShuffleUpsample: 1x1 conv -> SiLU -> PixelShuffle(2) fused in one GEMM epilogue (:603-631)."""
-        sd, R = self.sd, self.R
+        sd, R = self.sdc, self.R
         Wu = sd[p + '.net.0.weight'][:, :, 0, 0]                               # [c'*4 + r, C]
         Wu = Wu.view(dout, 4, x.C).permute(1, 0, 2).reshape(4 * dout, x.C)     # -> [r*C' + c', C]
         bu = sd[p + '.net.0.bias'].view(dout, 4).permute(1, 0).reshape(-1)
@@ -340,7 +399,7 @@ class UnetPlan:
 
     # ------------------------------------------------------------------ plan
     def _build(self):
-        a, sd, R, B, H, W = self.arch, self.sd, self.R, self.B, self.H, self.W
+        a, sd, R, B, H, W = self.arch, self.sdc, self.R, self.B, self.H, self.W
         # FiLM table: every ResnetBlock's time_mlp Linear batched into one GEMM per step (:711-714, :739-741)
         names = [k[:-len('.time_mlp.1.weight')] for k in param_table(a) if k.endswith('.time_mlp.1.weight')]
         self.film_offsets, off = {}, 0
@@ -362,8 +421,8 @@ class UnetPlan:
         imgs += [None] * (3 - len(imgs))
         self._add('b200_im2col_init3', *[v for im in imgs for v in ((im.data_ptr(), a.channels) if im is not None else (None, 0))],
                   B, H, W, ks, patches.ptr, Kinit)
-        Wi = torch.zeros(a.init_dim, ks, ks, Cin, device=self.device)
-        bi = torch.zeros(a.init_dim, device=self.device)
+        Wi = torch.zeros(a.init_dim, ks, ks, Cin)
+        bi = torch.zeros(a.init_dim)
         row = 0
         for i, (k, ds) in enumerate(zip(a.init_kernels, a.init_dim_scales)):
             pre = f'init_conv.convs.{i}' if a.init_cross_embed else 'init_conv'
@@ -427,7 +486,7 @@ class UnetPlan:
         Wf, bf = sd['final_conv.weight'], sd['final_conv.bias']
         if a.lowres_cond:                                                      # cat((x, lowres_cond_img)) before final_conv (:1722-1723)
             self.lowres_rows = self._new(R * H * W, 8, H, W)
-            Wpad = torch.zeros(Wf.shape[0], a.dim + 8, *Wf.shape[2:], device=self.device)
+            Wpad = torch.zeros(Wf.shape[0], a.dim + 8, *Wf.shape[2:])
             Wpad[:, :a.dim + a.channels] = Wf
             self._conv([x, self.lowres_rows], Wpad, a.channels_out, self.pred, split=[a.dim, 8], bias=bf, out_mode=_lib.OUT_F32_NCHW)
         else:
@@ -437,11 +496,16 @@ class UnetPlan:
         ops = list(stem)
         if self._jobs:
             jobs = (TimeRowJob * len(self._jobs))(*self._jobs)
-            jb = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(self.device)
-            self._keep.append(jb)
+            jb = self._wts.put(torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8))
             max_elems = max(j.rows * j.width for j in self._jobs)
             ops.append((self.lib.b200_update_time_rows, (jb.data_ptr(), len(self._jobs), self.slots.data_ptr(), R, max_elems), 'b200_update_time_rows'))
         self._ops = ops + body
+        # staged host chunks -> device (one memcpy per chunk), then the few constant rows that live inside activation buffers
+        self._wts.flush()
+        for dst, src in self._post:
+            dst.copy_(src.expand_as(dst))
+        self._post = None
+        del self.sdc
         # our kernel launches per U-Net evaluation (b200_gca_gate = logits + pool + combine + 2 MLP kernels)
         self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4 + \
             sum(1 for c in self._keep if getattr(c, 'desc', {}).get('ksplit', 1) > 1)      # + split-K finishing kernels (GemmCall.desc)
@@ -677,13 +741,10 @@ class Unet(nn.Module):
         unet.load_state_dict(state_dict)
         return unet
 
-    def load_state_dict(self, *args, **kwargs):
-        self._plans.clear()                                                    # packed weights are stale
-        return super().load_state_dict(*args, **kwargs)
-
-    def _apply(self, fn, *args, **kwargs):
-        self._plans.clear()
-        return super()._apply(fn, *args, **kwargs)
+    def _fingerprint(self):
+        """Identity of the parameter storage a plan was packed from: (data_ptr, in-place version counter) of every parameter.
+        load_state_dict (also through a parent module's), .to(device), p.data.copy_() / EMA swaps all change it."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     # --- plans ---------------------------------------------------------------------------------
     def plan(self, R, B, H, W, n_slots, device=None):
@@ -694,6 +755,9 @@ class Unet(nn.Module):
                                  'move the module to cuda first')
         _lib.require_device(device.index if device.index is not None else torch.cuda.current_device())
         key = (R, B, H, W, n_slots, str(device), self._gemm_impl)
+        fp = self._fingerprint()
+        if any(pl.fingerprint != fp for pl in self._plans.values()):            # parameters moved or were updated in place: packed weights are stale
+            self._plans.clear()
         if key not in self._plans:
             with torch.no_grad(), torch.cuda.device(device):
                 self._plans[key] = UnetPlan(self, R, B, H, W, n_slots, device, self._gemm_impl)

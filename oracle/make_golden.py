@@ -271,13 +271,121 @@ def main():
                     timesteps=4, cond_scale=2., seed_ddpm=53, out_ddpm=r_scs, num_sample_steps=3, sigma_max=2., seed_edm=59, out_edm=r_sce),
                os.path.join(out_dir, 'self_cond_dim32.pt'))
 
+    # ---------------------------------------------------------------- 5e. pred_objectives 'v' / 'x_start' (imagen_pytorch.py:2085-2090, :308-312)
+    obj = {}
+    for objective, seed in (('v', 71), ('x_start', 73)):
+        im_o = ref.Imagen(unets=ref.Unet(**base_kw), image_sizes=32, timesteps=4, text_embed_dim=64, pred_objectives=objective)
+        im_o.unets[0].load_state_dict(sd)
+        torch.manual_seed(seed)
+        r_o = im_o.sample(text_embeds=te, cond_scale=2., use_tqdm=False)
+        torch.manual_seed(seed)
+        o_o = sampler_ref.imagen_sample([(sd, cfg)], (32,), text_embeds=te, timesteps=4, cond_scale=2., pred_objectives=objective)
+        d = _maxdiff(r_o, o_o)
+        print(f'[ddpm objective {objective}] ref-vs-oracle max|d| = {d:.3e}')
+        assert d < 1e-4
+        obj[objective] = dict(seed=seed, out=r_o)
+    torch.save(dict(kwargs=base_kw, wseed=0, text_embeds=te, timesteps=4, cond_scale=2., objectives=obj),
+               os.path.join(out_dir, 'ddpm_objectives_dim32.pt'))
+
+    # ---------------------------------------------------------------- 5f. BASELINE.json shapes: the oracle pinned against the live reference
+    # (i) configs[1] architecture: Unet(dim=128) @64x64 with (256, 768) text embeddings -- cond / null / CFG-3 forward.
+    # Inputs and weights are rebuilt from seeds in the tests (synth_state_dict over the key->shape contract), only outputs are stored.
+    def seeded_inputs(seed, B, size, L=256, D=768, ragged=True):
+        gg = torch.Generator().manual_seed(seed)
+        x_ = torch.randn(B, 3, size, size, generator=gg)
+        te_ = torch.randn(B, L, D, generator=gg)
+        if ragged and B > 1:
+            te_[1, L // 3:] = 0.
+        return x_, te_, torch.any(te_ != 0., dim=-1)
+
+    big = {}
+    for name, kw, wseed, iseed in (('dim128', dict(dim=128), 11, 101), ('dim192', dict(dim=192), 12, 102)):
+        ub, sdb, cfgb = build('base_' + name, kw, wseed)
+        Bb = 2 if name == 'dim128' else 1
+        xb, teb, tmb = seeded_inputs(iseed, Bb, 64)
+        tb = torch.tensor([0.8, -1.3])[:Bb]
+        with torch.no_grad():
+            r1 = ub(xb, tb, text_embeds=teb, text_mask=tmb)
+            o1 = unet_ref.unet_forward(sdb, cfgb, xb, tb, text_embeds=teb, text_mask=tmb)
+            entry = dict(kwargs=kw, wseed=wseed, iseed=iseed, B=Bb, t=tb, out_cond=r1)
+            d = _maxdiff(r1, o1)
+            print(f'[unet {name} @64 cond] ref-vs-oracle max|d| = {d:.3e}  (|ref|max {r1.abs().max():.3f})')
+            assert d < 2e-5 * max(1., r1.abs().max().item())
+            if name == 'dim128':
+                r0 = ub(xb, tb, text_embeds=teb, text_mask=tmb, cond_drop_prob=1.)
+                o0 = unet_ref.unet_forward(sdb, cfgb, xb, tb, text_embeds=teb, text_mask=tmb, cond_drop_prob=1.)
+                d = _maxdiff(r0, o0)
+                print(f'[unet {name} @64 null] ref-vs-oracle max|d| = {d:.3e}')
+                assert d < 2e-5 * max(1., r0.abs().max().item())
+                entry.update(out_null=r0, out_cfg3=r0 + (r1 - r0) * 3.)
+        big[name] = entry
+        del ub, sdb
+    # (ii) configs[3] second stage: SRUnet256(lowres_cond=True) forward at 256 x 256, B = 1
+    torch.manual_seed(0)
+    usr = ref.SRUnet256(lowres_cond=True)
+    shp = {k: tuple(v.shape) for k, v in usr.state_dict().items()}
+    sdsr = unet_ref.synth_state_dict(shp, seed=13)
+    usr.load_state_dict(sdsr)
+    usr.eval()
+    sr256_kw = dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=(2, 4, 8, 8), layer_attns=(False, False, False, True),
+                    layer_cross_attns=(False, False, False, True), attn_heads=8, ff_mult=2., memory_efficient=True)
+    cfgsr = unet_ref.unet_config(**sr256_kw, lowres_cond=True)
+    xr, ter, tmr = seeded_inputs(103, 1, 256)
+    lowr = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(104))
+    with torch.no_grad():
+        rr = usr(xr, torch.tensor([0.4]), text_embeds=ter, text_mask=tmr, lowres_cond_img=lowr, lowres_noise_times=torch.tensor([0.7093]))
+        orr = unet_ref.unet_forward(sdsr, cfgsr, xr, torch.tensor([0.4]), text_embeds=ter, text_mask=tmr, lowres_cond_img=lowr,
+                                    lowres_noise_times=torch.tensor([0.7093]))
+    d = _maxdiff(rr, orr)
+    print(f'[SRUnet256 @256] ref-vs-oracle max|d| = {d:.3e}  (|ref|max {rr.abs().max():.3f})')
+    assert d < 2e-5 * max(1., rr.abs().max().item())
+    big['srunet256'] = dict(kwargs=sr256_kw, wseed=13, iseed=103, lseed=104, t=torch.tensor([0.4]), lowres_noise_times=torch.tensor([0.7093]), out=rr)
+    del usr, sdsr
+    # (iii) SURVEY.md 8f.1: the SRUnet1024 architecture through the upscale-only entry (start_at_unet_number = 2) at 64 -> 128
+    sr1024_kw = dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=(2, 4, 8, 8), layer_attns=False,
+                     layer_cross_attns=(False, False, False, True), attn_heads=8, ff_mult=2., memory_efficient=True)
+    torch.manual_seed(0)
+    u1k = ref.SRUnet1024()
+    im1k = ref.Imagen(unets=(ref.Unet(**base_kw), u1k), image_sizes=(64, 128), timesteps=3, text_embed_dim=64)
+    shp1k = {k: tuple(v.shape) for k, v in im1k.unets[1].state_dict().items()}
+    sd1k = unet_ref.synth_state_dict(shp1k, seed=14)
+    im1k.unets[1].load_state_dict(sd1k)
+    cfg1k = unet_ref.unet_config(**sr1024_kw, lowres_cond=True, text_embed_dim=64)
+    start = torch.rand(B, 3, 64, 64, generator=torch.Generator().manual_seed(105))
+    torch.manual_seed(79)
+    r1k = im1k.sample(text_embeds=te, cond_scale=2., use_tqdm=False, start_at_unet_number=2, start_image_or_video=start)
+    torch.manual_seed(79)
+    o1k = sampler_ref.imagen_sample([(sd, cfg), (sd1k, cfg1k)], (64, 128), text_embeds=te, timesteps=3, cond_scale=2.,
+                                    start_at_unet_number=2, start_image=start)
+    d = _maxdiff(r1k, o1k)
+    print(f'[SRUnet1024 arch, upscale-only 64->128] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-4
+    big['srunet1024_upscale'] = dict(kwargs=sr1024_kw, wseed=14, text_embeds=te, start_seed=105, seed=79, timesteps=3, cond_scale=2., out=r1k)
+    shapes_out['srunet1024_t64'] = shp1k
+    # (iv) BASELINE.json configs[0]: base Unet dim=32 dim_mults=(1,2,4,8) @64x64, bs=2, 50 DDPM steps, text (256, 768), reference p_sample_loop
+    kw0 = dict(dim=32, dim_mults=(1, 2, 4, 8))
+    u0, sd0, cfg0 = build('base_dim32_full', kw0, 15)
+    x0_, te0, _ = seeded_inputs(106, 2, 64)
+    im0 = ref.Imagen(unets=ref.Unet(**kw0), image_sizes=64, timesteps=50)
+    im0.unets[0].load_state_dict(sd0)
+    torch.manual_seed(83)
+    r50 = im0.sample(text_embeds=te0, cond_scale=1., use_tqdm=False)
+    torch.manual_seed(83)
+    o50 = sampler_ref.imagen_sample([(sd0, cfg0)], (64,), text_embeds=te0, timesteps=50, cond_scale=1.)
+    d = _maxdiff(r50, o50)
+    print(f'[configs[0]: dim32 @64, bs 2, 50 DDPM steps] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-3
+    big['cfg0_50steps'] = dict(kwargs=kw0, wseed=15, iseed=106, seed=83, timesteps=50, out=r50)
+    torch.save(big, os.path.join(out_dir, 'baseline_shapes.pt'))
+
     # ---------------------------------------------------------------- 6. schedule / scalar known answers
     tt = torch.tensor([1., .75, .5, .25, 0., 0.2])
     torch.save(dict(t=tt, cosine=ref.imagen_pytorch.alpha_cosine_log_snr(tt), linear=ref.imagen_pytorch.beta_linear_log_snr(tt),
                     edm_sigmas=el.sample_schedule(4, 7, 0.002, 80)), os.path.join(out_dir, 'schedules.pt'))
 
     # ---------------------------------------------------------------- 7. state_dict key/shape contract of the default configs
-    contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr'], 'test_selfcond': shapes_out['selfcond']}
+    contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr'], 'test_selfcond': shapes_out['selfcond'],
+                'base_dim192': shapes_out['base_dim192'], 'srunet1024_t64': shapes_out['srunet1024_t64']}
     for name, kw in (('base_dim128', dict(dim=128)), ('base_dim32', dict(dim=32, dim_mults=(1, 2, 4, 8)))):
         torch.manual_seed(0)
         m = ref.Unet(**kw)

@@ -154,9 +154,9 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
                   noise_schedules=('cosine',), lowres_sample_noise_level=0.2, dynamic_thresholding=True,
                   pred_objectives='noise', stop_at_unet_number=None, return_all_unet_outputs=False, trace=None,
                   randn=torch.randn, init_images=None, skip_steps=None, inpaint_images=None, inpaint_masks=None,
-                  inpaint_resample_times=5):
-    """Imagen.sample (imagen_pytorch.py:2291-2498), text_embeds path, no video/inpaint.
-    unets: list of (state_dict, cfg)."""
+                  inpaint_resample_times=5, start_at_unet_number=1, start_image=None):
+    """Imagen.sample (imagen_pytorch.py:2291-2498), text_embeds path, no video.
+    unets: list of (state_dict, cfg).  start_at_unet_number / start_image: the upscale-only entry (:2396-2403)."""
     n = len(unets)
     timesteps = unet_ref._tup(timesteps, n)
     cond_scale = unet_ref._tup(cond_scale, n)
@@ -171,7 +171,12 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
     init_images = [None if im is None else im * 2 - 1 for im in unet_ref._tup(init_images, n)]   # :2385-2386 (normalize_img)
     skip_steps = unet_ref._tup(skip_steps, n)
     outputs, img = [], None
+    if start_at_unet_number > 1:                                               # :2396-2403
+        assert start_image is not None, 'starting image or video must be supplied if only doing upscaling'
+        img = resize_nearest(start_image, image_sizes[start_at_unet_number - 2])
     for i, ((sd, cfg), size) in enumerate(zip(unets, image_sizes)):
+        if i + 1 < start_at_unet_number:                                       # :2412-2414
+            continue
         kw = dict(text_embeds=text_embeds, text_mask=text_masks)
         lowres_log_snr = None
         opt = dict(skip_steps=skip_steps[i], inpaint_resample_times=inpaint_resample_times)

@@ -101,3 +101,29 @@ def test_sample_argument_validation_mirrors_reference():
         im.sample(text_embeds=torch.randn(1, 8, 64), cond_images=torch.zeros(1, 3, 16, 16), use_tqdm=False)                      # out of the hot path
     with pytest.raises(AssertionError):                                           # inpainting batch must match the text batch (:2343-2350)
         im.sample(text_embeds=torch.randn(1, 8, 64), inpaint_images=torch.zeros(2, 3, 16, 16), inpaint_masks=torch.zeros(2, 16, 16), use_tqdm=False)
+
+
+def test_plan_compiles_on_the_meta_device_without_kernels():
+    """The launch-plan compiler (weight packing through the staged host arena, activation arena, launch list) is pure host
+    logic: build it on torch's meta device and check the bookkeeping."""
+    import imagen_pytorch_b200 as b2
+    from imagen_pytorch_b200.unet import UnetPlan
+    u = b2.Unet(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24)
+    plan = UnetPlan(u, 4, 2, 32, 32, 6, torch.device('meta'))
+    assert plan.n_launches > 100 and len(plan._ops) > 100
+    assert plan.fingerprint == u._fingerprint()
+    assert plan.n_ctx == 2 + 32 + 4                           # time tokens + perceiver latents (32 + 4 mean-pooled)
+    # every weight operand lives in the staged arena, every activation in the zero-filled one: a handful of chunks in total
+    assert len(plan._wts.chunks) <= 4 and len(plan._act.chunks) <= 4
+    with torch.no_grad():
+        next(u.parameters()).add_(1.0)                        # in-place update -> fingerprint changes -> plans are rebuilt
+    assert plan.fingerprint != u._fingerprint()
+
+
+def test_unet_plan_cache_survives_noop_module_moves():
+    import imagen_pytorch_b200 as b2
+    u = b2.Unet(dim=32, dim_mults=(1, 2))
+    fp = u._fingerprint()
+    u._plans['sentinel'] = type('P', (), {'fingerprint': fp})()
+    u.to('cpu')                                               # Imagen.sample() calls unets.to(device) on every call
+    assert 'sentinel' in u._plans and u._fingerprint() == fp

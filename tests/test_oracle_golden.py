@@ -143,3 +143,32 @@ def test_schedule_known_answers():
     assert abs(sampler_ref.alpha_cosine_log_snr(torch.tensor([0.5])).item() + 0.0249) < 1e-3
     assert abs(sampler_ref.beta_linear_log_snr(torch.tensor([0.2])).item() - 0.7093) < 1e-3
     assert abs(sampler_ref.edm_sample_schedule(4, 7, 0.002, 80)[1].item() - 9.7232) < 1e-2
+
+
+def test_pred_objectives_v_and_x_start_match_reference_golden():
+    """pred_objective 'v' / 'x_start' (imagen_pytorch.py:2085-2090, :308-312) of the oracle's DDPM loop against the live reference."""
+    g = load_golden('ddpm_objectives_dim32.pt')
+    sd = synth_weights('test_base', g['wseed'])
+    cfg = unet_ref.unet_config(**g['kwargs'])
+    outs = {}
+    for objective, e in g['objectives'].items():
+        torch.manual_seed(e['seed'])
+        with torch.no_grad():
+            outs[objective] = sampler_ref.imagen_sample([(sd, cfg)], (32,), text_embeds=g['text_embeds'], timesteps=g['timesteps'],
+                                                        cond_scale=g['cond_scale'], pred_objectives=objective)
+        assert (outs[objective] - e['out']).abs().max() < 1e-4
+    assert (outs['v'] - outs['x_start']).abs().mean() > 1e-2      # two different parameterisations, two different images
+
+
+def test_baseline_shape_fixture_is_complete():
+    """tests/golden/baseline_shapes.pt holds the live reference's outputs at the BASELINE.json shapes (the GPU suite replays them);
+    here: the fixture's entries and the key->shape contracts they rebuild their weights from."""
+    from tests.helpers import contract
+    g, c = load_golden('baseline_shapes.pt'), contract()
+    assert set(g) == {'dim128', 'dim192', 'srunet256', 'srunet1024_upscale', 'cfg0_50steps'}
+    assert g['dim128']['out_cond'].shape == (2, 3, 64, 64) and g['dim192']['out_cond'].shape == (1, 3, 64, 64)
+    assert g['srunet256']['out'].shape == (1, 3, 256, 256) and g['srunet1024_upscale']['out'].shape == (2, 3, 128, 128)
+    assert g['cfg0_50steps']['out'].shape == (2, 3, 64, 64) and g['cfg0_50steps']['timesteps'] == 50
+    for name in ('base_dim128', 'base_dim192', 'base_dim32', 'srunet256', 'srunet1024_t64'):
+        assert name in c and len(c[name]) > 100
+    assert torch.allclose(g['dim128']['out_cfg3'], g['dim128']['out_null'] + (g['dim128']['out_cond'] - g['dim128']['out_null']) * 3.)

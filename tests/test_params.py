@@ -9,6 +9,9 @@ from tests.helpers import contract, synth_weights
 CASES = {
     'base_dim128': dict(dim=128),
     'base_dim32': dict(dim=32, dim_mults=(1, 2, 4, 8)),
+    'base_dim192': dict(dim=192),
+    'srunet1024_t64': dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=(2, 4, 8, 8), layer_attns=False, layer_cross_attns=(False, False, False, True),
+                           attn_heads=8, ff_mult=2., memory_efficient=True, lowres_cond=True, text_embed_dim=64),
     'test_base': dict(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24),
     'test_sr': dict(dim=32, dim_mults=(1, 2, 4), text_embed_dim=64, max_text_len=24, num_resnet_blocks=(1, 2, 2),
                     layer_attns=(False, False, True), layer_cross_attns=(False, False, True), memory_efficient=True, lowres_cond=True),

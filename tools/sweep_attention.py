@@ -5,7 +5,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = {0: 'nw4', 1: 'nw8', 2: 'nw8+pf', 3: 'nw16', 4: 'nw16+pf', 5: 'nw8+wa', 6: 'nw8+pf+wa', 7: 'nw16+pf+wa', 8: 'nw4+wa', 9: 'pingpong', 10: 'pp+poly1/4', 11: 'pp+poly1/2', 12: 'pp16', 13: 'pp16+poly1/4'}
+NAMES = {0: 'nw4', 1: 'nw8', 2: 'nw8+pf', 3: 'nw16', 4: 'nw16+pf', 5: 'nw8+wa', 6: 'nw8+pf+wa', 7: 'nw16+pf+wa', 8: 'nw4+wa', 9: 'pingpong', 10: 'pp+poly1/4', 11: 'pp+poly1/2', 12: 'pp16', 13: 'pp16+poly1/4',
+         20: 'pt16', 21: 'pt16+poly1/8', 22: 'pt16+poly1/5', 23: 'pt16+poly1/4', 24: 'pt16+poly1/3', 25: 'pt16+poly1/2', 26: 'pt8', 27: 'pt8+poly1/4', 28: 'pt8+poly1/3'}
 CODE = '''
 import sys, torch
 sys.path.insert(0, %r)
@@ -14,24 +15,28 @@ from bench import time_attention_kernel
 from imagen_pytorch_b200 import _lib
 dev = torch.device('cuda')
 ms = time_attention_kernel(32, dev, iters=5)
-# correctness vs the mma.sync kernel on a small problem
-B, rows, nk = 2, 8 * 256, 256 + 39 + 128
-q = (F.normalize(torch.randn(B, rows, 64, device=dev), dim=-1) * 8 * 1.4426950408889634).to(torch.bfloat16)
-k = F.normalize(torch.randn(B, nk, 64, device=dev), dim=-1).to(torch.bfloat16)
-v = torch.randn(B, nk, 64, device=dev).to(torch.bfloat16)
-o1, o2 = torch.zeros_like(q), torch.zeros_like(q)
-st = torch.cuda.current_stream().cuda_stream
-_lib.call('b200_attention', q.data_ptr(), o1.data_ptr(), rows * 64, 0, 64, rows, k.data_ptr(), v.data_ptr(), nk * 64, 0, 64, nk, B, 1, 11.8, st)
-_lib.call('b200_attention', q.data_ptr(), o2.data_ptr(), rows * 64, 0, 64, rows, k.data_ptr(), v.data_ptr(), nk * 64, 0, 64, nk, B, 1, 0.0, st)
-torch.cuda.synchronize()
-print('RESULT %%.4f ms  %%.1f TFLOP/s  maxdiff %%.4f' %% (ms, 1109.98 / ms, (o1.float() - o2.float()).abs().max().item()))
+# correctness vs the mma.sync kernel on small problems: last tile with 39 keys (dead second half), 100 keys (partial second half), full
+md = 0.0
+for nk in (256 + 39 + 128, 256 + 100, 384, 512 + 64, 257):
+    B, rows = 2, 8 * 256 + 64
+    q = (F.normalize(torch.randn(B, rows, 64, device=dev), dim=-1) * 8 * 1.4426950408889634).to(torch.bfloat16)
+    k = F.normalize(torch.randn(B, nk, 64, device=dev), dim=-1).to(torch.bfloat16)
+    v = torch.randn(B, nk, 64, device=dev).to(torch.bfloat16)
+    o1, o2 = torch.zeros_like(q), torch.zeros_like(q)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call('b200_attention', q.data_ptr(), o1.data_ptr(), rows * 64, 0, 64, rows, k.data_ptr(), v.data_ptr(), nk * 64, 0, 64, nk, B, 1, 11.8, st)
+    _lib.call('b200_attention', q.data_ptr(), o2.data_ptr(), rows * 64, 0, 64, rows, k.data_ptr(), v.data_ptr(), nk * 64, 0, 64, nk, B, 1, 0.0, st)
+    torch.cuda.synchronize()
+    md = max(md, (o1.float() - o2.float()).abs().max().item())
+print('RESULT %%.4f ms  %%.1f TFLOP/s  maxdiff %%.4f' %% (ms, 1109.98 / ms, md))
 ''' % ROOT
 
-for var in sorted(NAMES):
+only = [int(v) for v in os.environ.get('SWEEP_VARIANTS', '').split(',') if v.strip()]
+for var in (only or sorted(NAMES)):
     env = dict(os.environ, B200_IMAGEN_FA_VARIANT=str(var))
     try:
         out = subprocess.run([sys.executable, '-c', CODE], env=env, capture_output=True, text=True, timeout=300)
         res = [l for l in out.stdout.splitlines() if l.startswith('RESULT')]
-        print(f'variant {var} {NAMES[var]:12s}', res[0] if res else ('FAILED ' + out.stderr[-300:]))
+        print(f'variant {var} {NAMES.get(var, "?"):12s}', res[0] if res else ('FAILED ' + out.stderr[-300:]))
     except subprocess.TimeoutExpired:
         print(f'variant {var} {NAMES[var]:12s} TIMEOUT')
