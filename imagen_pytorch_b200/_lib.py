@@ -15,6 +15,8 @@ MAX_SRC, MAX_SEG = 4, 24
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 OUT_BF16, OUT_PIXEL_SHUFFLE, OUT_F32_NCHW, OUT_F32 = 0, 1, 2, 3
 IMPL_TCGEN05, IMPL_SIMT_CHECKER = 0, 1
+NORM_NONE, NORM_LN, NORM_RMS_FILM_SILU = 0, 1, 2
+ABI_VERSION = 2
 
 
 class Src(C.Structure):
@@ -33,6 +35,9 @@ class Epilogue(C.Structure):
         ('out2', C.c_void_p), ('ldc2', C.c_int32), ('split_col', C.c_int32),
         ('rows_per_group', C.c_int32), ('group_stride', C.c_int32), ('row_offset', C.c_int32),
         ('l2_cols', C.c_int32), ('l2_scale', C.c_void_p), ('ps_C', C.c_int32), ('dup_rows', C.c_int32),
+        # ABI v2: per-row norms fused into the epilogue (include/b200_imagen.h)
+        ('norm1', C.c_int32), ('norm1_g', C.c_void_p), ('norm2', C.c_int32), ('norm2_g', C.c_void_p), ('film', C.c_void_p),
+        ('film_ld', C.c_int32), ('rows_per_sample', C.c_int32), ('out_norm', C.c_void_p), ('ld_norm', C.c_int32),
     ]
 
 
@@ -109,7 +114,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
-    if lib.b200_abi_version() != 1:
+    if lib.b200_abi_version() != ABI_VERSION:
         raise B200Error('libb200imagen.so ABI version mismatch')
     _lib = lib
     return lib

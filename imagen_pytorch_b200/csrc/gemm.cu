@@ -34,8 +34,13 @@ struct EpiDev {
   void* out;
   void* out2;
   const float* l2_scale;
+  const float* norm1_g;
+  const float* norm2_g;
+  const float* film;
+  void* out_norm;
   float out_scale;
   int act, ldr, out_mode, ldc, ldc2, split_col, rows_per_group, group_stride, row_offset, l2_cols, ps_C, dup_rows;
+  int norm1, norm2, film_ld, rows_per_sample, ld_norm;
 };
 
 struct GemmParams {
@@ -534,12 +539,170 @@ __device__ __forceinline__ void tmem_wait_regs16(float* v) {
   for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(v[i]));
 }
 
+// ---- norm-fusing epilogue (b200_epilogue.norm1 / norm2) -----------------------------------------------------------------
+// One N tile spans all channels, so a thread (= accumulator row = one pixel / token) sees its whole row in TMEM, BNH columns per
+// epilogue warp.  Row statistics are reduced across the HALVES warps that share a TMEM lane quarter through a small shared-memory
+// exchange + a named barrier per quarter; the accumulator is simply re-read from TMEM for every pass (TMEM reads are cheap, the
+// GEMMs this is used on are bound by the MMA pipe or by HBM, not by the epilogue):
+//   [norm1] pass: sum -> mean, pass: centred sum of squares -> rstd          (two-pass LayerNorm, fp32)
+//   [norm2] pass: w = norm1(v) + residual; sum(w), sum(w^2)                  (LayerNorm: var = E[w^2] - mean^2; RMS: |w|_2)
+//   final pass  : w -> out (raw, optional), norm2(w) -> out_norm; both through the warp's staging tile -> coalesced stores.
+// Exchange slots are indexed by (tile parity, round) so that a fast warp's next-tile write can never overtake a slow warp's read.
+
+__device__ __forceinline__ void flush32_to(__nv_bfloat16* base, int ld, const GemmParams& p, const RowInfo& ri, int ng, uint32_t stage, uint32_t meta,
+                                           int lane) {
+  const long long my_dst = ri.valid ? reinterpret_cast<long long>(base + ri.row * (long long)ld + ng) : 0ll;
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(meta + (uint32_t)lane * 16u), "r"((uint32_t)my_dst), "r"((uint32_t)(my_dst >> 32)) : "memory");
+  const int rs = lane >> 2, ch = lane & 3;
+  const uint32_t rd = stage + (uint32_t)rs * 64u + (uint32_t)((ch ^ ((rs >> 1) & 3)) << 4);
+  __syncwarp();
+  uint4 u[4];
+  uint32_t m0[4], m1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    u[r] = ld_shared_v4(rd + (uint32_t)r * 512u);
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(m0[r]), "=r"(m1[r]) : "r"(meta + (uint32_t)(8 * r + rs) * 16u) : "memory");
+  }
+  if (ng + ch * 8 < p.N) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long d = (long long)(((unsigned long long)m1[r] << 32) | m0[r]);
+      if (d != 0) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d) + ch * 8) = u[r];
+    }
+  }
+  __syncwarp();
+}
+
+template <int BNH, int HALVES, class Load32, class Wait32>
+__device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo& ri, int n0, uint32_t stage, uint32_t meta, float2* xch, int parity,
+                                              int q, int half, int lane, Load32 load32, Wait32 wait32) {
+  static_assert(BNH % 32 == 0, "32-column passes");
+  const EpiDev& e = p.epi;
+  const int r = q * 32 + lane;
+  const float invN = 1.f / (float)p.N;
+  auto exchange = [&](int round, float a, float b) -> float2 {
+    if (HALVES == 1) return make_float2(a, b);
+    float2* reg = xch + (size_t)((parity * 3 + round) * HALVES) * 128;
+    reg[half * 128 + r] = make_float2(a, b);
+    asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "n"(32 * HALVES) : "memory");   // the HALVES warps of this lane quarter
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < HALVES; ++h) {      // same order in every warp: bitwise identical statistics
+      const float2 t = reg[h * 128 + r];
+      s.x += t.x; s.y += t.y;
+    }
+    return s;
+  };
+  float va[32];
+  auto base = [&](int c) {                  // v = act(acc + bias) * out_scale of columns [n0 + c, +32)
+    load32(c, va);
+    wait32(va);
+    epi_math32(e, n0 + c, va);
+  };
+  float mean1 = 0.f, rstd1 = 1.f;
+  if (e.norm1) {
+    float s = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BNH; c += 32) {
+      if (n0 + c >= p.N) break;
+      base(c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += va[j];
+    }
+    mean1 = exchange(0, s, 0.f).x * invN;
+    float vs = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BNH; c += 32) {
+      if (n0 + c >= p.N) break;
+      base(c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = va[j] - mean1; vs += d * d; }
+    }
+    rstd1 = rsqrtf(exchange(1, vs, 0.f).x * invN + 1e-5f);
+  }
+  const __nv_bfloat16* rrow = (e.residual != nullptr && ri.valid) ? e.residual + ri.row * (long long)e.ldr : nullptr;
+  auto wval = [&](int c) {                  // w = norm1(v) + residual
+    base(c);
+    const int n = n0 + c;
+    if (e.norm1) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm1_g + n + j));
+        va[j] = (va[j] - mean1) * rstd1 * g4.x; va[j + 1] = (va[j + 1] - mean1) * rstd1 * g4.y;
+        va[j + 2] = (va[j + 2] - mean1) * rstd1 * g4.z; va[j + 3] = (va[j + 3] - mean1) * rstd1 * g4.w;
+      }
+    }
+    if (rrow != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(rrow + n + j), f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) va[j + t] += f[t];
+      }
+    }
+  };
+  float m2 = 0.f, k2 = 1.f;
+  if (e.norm2) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BNH; c += 32) {
+      if (n0 + c >= p.N) break;
+      wval(c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s += va[j]; ss += va[j] * va[j]; }
+    }
+    const float2 t = exchange(2, s, ss);
+    if (e.norm2 == 1) {
+      m2 = t.x * invN;
+      k2 = rsqrtf(fmaxf(t.y * invN - m2 * m2, 0.f) + 1e-5f);
+    } else {
+      k2 = 1.f / fmaxf(sqrtf(t.y), 1e-12f);
+    }
+  }
+  const float* film = nullptr;
+  if (e.norm2 == 2 && e.film != nullptr) film = e.film + (long long)((unsigned)ri.row / (unsigned)e.rows_per_sample) * e.film_ld;
+#pragma unroll 1
+  for (int c = 0; c < BNH; c += 32) {
+    const int n = n0 + c;
+    if (n >= p.N) break;
+    wval(c);
+    if (e.out != nullptr) {
+      stage32(va, stage, lane);
+      flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n, stage, meta, lane);
+    }
+    if (e.norm2) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm2_g + n + j));
+        va[j] = (va[j] - m2) * k2 * g4.x; va[j + 1] = (va[j + 1] - m2) * k2 * g4.y;
+        va[j + 2] = (va[j + 2] - m2) * k2 * g4.z; va[j + 3] = (va[j + 3] - m2) * k2 * g4.w;
+      }
+      if (e.norm2 == 2) {
+        if (film != nullptr && ri.valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(film + n + j));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(film + p.N + n + j));
+            va[j] = va[j] * (s4.x + 1.f) + b4.x; va[j + 1] = va[j + 1] * (s4.y + 1.f) + b4.y;
+            va[j + 2] = va[j + 2] * (s4.z + 1.f) + b4.z; va[j + 3] = va[j + 3] * (s4.w + 1.f) + b4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) va[j] = silu_f(va[j]);
+      }
+      stage32(va, stage, lane);
+      flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out_norm), e.ld_norm, p, ri, n, stage, meta, lane);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ tcgen05 kernel
 // Persistent: one CTA per SM loops over output tiles; the smem operand ring (TMA -> MMA) runs straight across
 // tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the MMAs of
 // tile i+1.
 
-template <int BN, int STAGES, bool STAGED, int NEPI>
+template <int BN, int STAGES, bool STAGED, int NEPI, bool NORM>
 __global__ void __launch_bounds__(64 + 32 * NEPI, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -668,7 +831,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const RowInTile rit = row_in_tile(p, q * 32 + lane);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tile_parity = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_parity ^= 1) {
       const int tt = (int)((unsigned)t / (unsigned)ksplit), split = t - tt * ksplit;
       const int tile = (int)((unsigned)tt / (unsigned)n_tiles_n), n0 = (tt - tile * n_tiles_n) * BN;
       RowInfo ri = tile_row(p, tile, rit);
@@ -677,7 +841,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
       if (!(p.debug & 1)) {
-        if constexpr (STAGED) {
+        if constexpr (NORM) {
+          static_assert(STAGED, "the norm epilogue stores through the staging tiles");
+          const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
+          float2* xch = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 1024 + NEPI * EPI_STAGE_BYTES);
+          epilogue_norm<BNH, HALVES>(p, ri, n0 + half * BNH, stg, stg + 2048u, xch, tile_parity, q, half, lane,
+                                     [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                                     [&](float* v) { tmem_wait_regs32(v); });
+        } else if constexpr (STAGED) {
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
           epilogue_staged<BNH, (NEPI <= 8)>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
                                [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
@@ -974,14 +1145,15 @@ int next_pow2(int v) {
   return r;
 }
 
-template <int BN, int STAGES, bool SIMPLE, int NEPI>
+template <int BN, int STAGES, bool SIMPLE, int NEPI, bool NORM = false>
 int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapO, const GemmParams& p, int ntiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + NEPI * EPI_STAGE_BYTES : 0) /*staging*/;
+  constexpr int smem = STAGES * (A_TILE_BYTES + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + (SIMPLE ? 768 + NEPI * EPI_STAGE_BYTES : 0) /*staging*/ +
+                       (NORM ? 6 * (NEPI / 4) * 128 * 8 : 0) /*row-statistics exchange*/;
   static_assert(smem <= 232448, "shared memory budget");
-  B200_SMEM_OPT_IN((conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI>), smem);
+  B200_SMEM_OPT_IN((conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI, NORM>), smem);
   const long long total = (long long)ntiles * (p.Npad / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
+  conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI, NORM><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
   B200_LAUNCH_OK();
   return B200_OK;
 }
@@ -1075,7 +1247,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   B200_REQUIRE(nsrc >= 1 && nsrc <= B200_MAX_SRC, "conv_gemm: nsrc %d out of range", nsrc);
   B200_REQUIRE(nseg >= 1 && nseg <= B200_MAX_SEG, "conv_gemm: nseg %d out of range", nseg);
   B200_REQUIRE(B > 0 && H > 0 && W > 0 && N > 0, "conv_gemm: bad shape B=%d H=%d W=%d N=%d", B, H, W, N);
-  B200_REQUIRE(epi != nullptr && epi->out != nullptr && w_packed != nullptr, "conv_gemm: null pointer");
+  B200_REQUIRE(epi != nullptr && w_packed != nullptr, "conv_gemm: null pointer");
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W;
@@ -1122,6 +1294,27 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   e.ldc2 = epi->ldc2; e.split_col = epi->split_col; e.rows_per_group = epi->rows_per_group;
   e.group_stride = epi->group_stride; e.row_offset = epi->row_offset; e.l2_cols = epi->l2_cols; e.ps_C = epi->ps_C;
   e.dup_rows = epi->dup_rows;
+  e.norm1 = epi->norm1; e.norm1_g = epi->norm1_g; e.norm2 = epi->norm2; e.norm2_g = epi->norm2_g; e.film = epi->film;
+  e.film_ld = epi->film_ld; e.rows_per_sample = epi->rows_per_sample; e.out_norm = epi->out_norm; e.ld_norm = epi->ld_norm;
+  const bool has_norm = e.norm1 != 0 || e.norm2 != 0;
+  if (has_norm) {
+    const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    B200_REQUIRE(impl == 0, "conv_gemm: the norm epilogue exists on the tcgen05 path only");
+    B200_REQUIRE(N >= 64 && N <= 256 && N % 32 == 0, "conv_gemm: norm epilogue needs one N tile over all channels (64 <= N <= 256, N %% 32 == 0), got N=%d", N);
+    B200_REQUIRE(e.out_mode == B200_OUT_BF16 && e.split_col == 0 && e.rows_per_group == 0 && e.l2_cols == 0 && e.dup_rows == 0,
+                 "conv_gemm: norm epilogue is incompatible with split / remap / l2 / dup outputs");
+    B200_REQUIRE((e.norm1 == 0 || e.norm1 == 1) && e.norm2 >= 0 && e.norm2 <= 2, "conv_gemm: bad norm1/norm2 %d/%d", e.norm1, e.norm2);
+    B200_REQUIRE(e.norm1 == 0 || (e.norm1_g != nullptr && al16(e.norm1_g)), "conv_gemm: norm1 needs a 16-byte aligned gain vector");
+    B200_REQUIRE(e.norm2 == 0 || (e.norm2_g != nullptr && al16(e.norm2_g) && e.out_norm != nullptr && al16(e.out_norm) && (e.ld_norm & 7) == 0),
+                 "conv_gemm: norm2 needs a gain vector and an aligned out_norm");
+    B200_REQUIRE(e.film == nullptr || (e.norm2 == 2 && al16(e.film) && (e.film_ld & 3) == 0 && e.rows_per_sample > 0), "conv_gemm: bad FiLM operands");
+    B200_REQUIRE(e.out != nullptr || e.norm2 != 0, "conv_gemm: norm epilogue without any output");
+    B200_REQUIRE(e.out == nullptr || ((e.ldc & 7) == 0 && al16(e.out)), "conv_gemm: norm epilogue needs an aligned out");
+    B200_REQUIRE(e.residual == nullptr || ((e.ldr & 7) == 0 && al16(e.residual)), "conv_gemm: norm epilogue needs an aligned residual");
+    B200_REQUIRE((long long)B * H * W < (1ll << 31), "conv_gemm: too many rows for the norm epilogue");
+  } else {
+    B200_REQUIRE(epi->out != nullptr, "conv_gemm: null output");
+  }
   B200_REQUIRE(e.out_mode >= 0 && e.out_mode <= 3, "conv_gemm: bad out_mode %d", e.out_mode);
   B200_REQUIRE(e.split_col % 64 == 0 && e.l2_cols % 64 == 0, "conv_gemm: split_col/l2_cols must be multiples of 64");
   B200_REQUIRE(e.l2_cols == 0 || p.Npad >= 64, "conv_gemm: l2norm epilogue needs N >= 64");
@@ -1156,7 +1349,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   EncodeTiledFn enc = get_encode_fn();
   B200_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled not available from the driver");
   // tile shape: CTA pairs (256 x BN per pair, B split across the pair) whenever there are >= 2 row tiles and >= 128 columns
-  const bool pair = pair_enabled() && ntiles >= 2 && p.Npad >= 128;
+  const bool pair = pair_enabled() && !has_norm && ntiles >= 2 && p.Npad >= 128;
   int BN;
   if (p.Npad <= 64) BN = p.Npad;
   else if (pair) BN = (p.Npad % 256 == 0 && (long long)((ntiles + 1) / 2) * (p.Npad / 256) >= sm_count() / 2) ? 256 : 128;
@@ -1168,8 +1361,9 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
     const double c128 = (double)((t128 + sms - 1) / sms) * (128.0 / 878.0), c256 = (double)((t256 + sms - 1) / sms) * (256.0 / 1398.0);
     BN = c256 <= c128 ? 256 : 128;
   } else BN = 128;
+  if (has_norm) BN = p.Npad;   // one tile spans all channels
   p.ksplit = 1;
-  const int ks = (!pair && f32_scratch != nullptr) ? splitk_factor(ntiles, p.Npad, total) : 1;   // caller-provided partial-tile workspace
+  const int ks = (!pair && !has_norm && f32_scratch != nullptr) ? splitk_factor(ntiles, p.Npad, total) : 1;   // caller-provided partial-tile workspace
   if (ks > 1) BN = 256;
   const int boxN = pair ? BN / 2 : BN;
   CUtensorMap maps[B200_MAX_SRC];
@@ -1202,7 +1396,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   p.tma_store = 0;
   {
     static const bool tma_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_TMA_STORE"); return ev == nullptr || atoi(ev) != 0; }();
-    if (tma_on && gemm_is_simple(p) && e.out_mode == B200_OUT_BF16 && e.residual == nullptr && e.split_col == 0 && e.rows_per_group == 0 &&
+    if (tma_on && !has_norm && gemm_is_simple(p) && e.out_mode == B200_OUT_BF16 && e.residual == nullptr && e.split_col == 0 && e.rows_per_group == 0 &&
         e.dup_rows == 0 && (((long long)e.ldc * 2) & 15) == 0) {
       // the 32 rows of one epilogue warp are a sub-box of the tile box {bw, bh, bb}
       const int sw_ = p.bw < 32 ? p.bw : 32;
@@ -1235,6 +1429,13 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
     conv_gemm_splitk_epilogue_kernel<64><<<(unsigned)ceil_div64(t2, 128), 128, 0, st>>>(p, reinterpret_cast<const float*>(f32_scratch), ks);
     B200_LAUNCH_OK();
     return B200_OK;
+  }
+  if (has_norm) {
+    switch (BN) {
+      case 64: return launch_tc2<64, 8, true, 4, true>(maps, mapB, mapO, p, ntiles, st);
+      case 128: return launch_tc2<128, 5, true, 8, true>(maps, mapB, mapO, p, ntiles, st);
+      default: return launch_tc2<256, 4, true, 8, true>(maps, mapB, mapO, p, ntiles, st);
+    }
   }
   if (pair) return BN == 256 ? launch_pair<256, 6>(maps, mapB, mapO, p, ntiles, st) : launch_pair<128, 8>(maps, mapB, mapO, p, ntiles, st);
   switch (BN) {

@@ -50,7 +50,8 @@ class GemmCall:
 
     def __init__(self, srcs, segs, grid, wpacked, N, out_ptr, *, bias=None, act=0, out_scale=1.0, residual=None, ldr=0,
                  out_mode=_lib.OUT_BF16, ldc=0, out2_ptr=None, ldc2=0, split_col=0, rows_per_group=0, group_stride=0, row_offset=0,
-                 l2_cols=0, l2_scale=None, ps_C=0, dup_rows=0, impl=_lib.IMPL_TCGEN05, scratch_ptr=None):
+                 l2_cols=0, l2_scale=None, ps_C=0, dup_rows=0, impl=_lib.IMPL_TCGEN05, scratch_ptr=None,
+                 norm1=0, norm1_g=None, norm2=0, norm2_g=None, film_ptr=None, film_ld=0, rows_per_sample=0, out_norm_ptr=None, ld_norm=0):
         """srcs: list of (ptr, C, ld); segs: list of (src, dh, dw); grid: (B, H, W) of the output pixel rows."""
         self.lib = _lib.load()
         self.keep = [wpacked, bias, l2_scale]
@@ -60,16 +61,42 @@ class GemmCall:
         e.bias = bias.data_ptr() if bias is not None else None
         e.act, e.out_scale = act, out_scale
         e.residual, e.ldr = residual, ldr
-        e.out_mode, e.out, e.ldc = out_mode, out_ptr, ldc
+        e.out_mode, e.out, e.ldc = out_mode, out_ptr, ldc       # out_ptr may be None when only the fused norm output is wanted
         e.out2, e.ldc2, e.split_col = out2_ptr, ldc2, split_col
         e.rows_per_group, e.group_stride, e.row_offset = rows_per_group, group_stride, row_offset
         e.l2_cols = l2_cols
         e.l2_scale = l2_scale.data_ptr() if l2_scale is not None else None
         e.ps_C, e.dup_rows = ps_C, dup_rows
         self.e = e
+        self.N, self.impl = N, impl
         self.desc = {'B': grid[0], 'H': grid[1], 'W': grid[2], 'N': N, 'nseg': len(segs), 'C': [c for (_, c, _) in srcs],
                      'K': sum(-(-srcs[g[0]][1] // 64) * 64 for g in segs), 'act': act, 'out_mode': out_mode}
         self.args = (self.sa, len(srcs), self.ga, len(segs), grid[0], grid[1], grid[2], wpacked.data_ptr(), N, C.byref(e), impl, scratch_ptr)
+        if norm1:
+            self.set_norm1(norm1_g)
+        if norm2:
+            self.set_norm2(norm2, norm2_g, out_norm_ptr, ld_norm, film_ptr=film_ptr, film_ld=film_ld, rows_per_sample=rows_per_sample)
+
+    # ---- per-row norms fused into the epilogue (b200_epilogue ABI v2).  The struct is passed by reference at every launch, so a
+    # consumer discovered later by the plan compiler can still attach its norm to an already recorded producer GEMM.
+    def norm_capable(self):
+        e = self.e
+        return (self.impl == _lib.IMPL_TCGEN05 and 64 <= self.N <= 256 and self.N % 32 == 0 and e.out_mode == _lib.OUT_BF16 and e.split_col == 0 and
+                e.rows_per_group == 0 and e.l2_cols == 0 and e.dup_rows == 0 and self.desc.get('ksplit', 1) == 1)
+
+    def set_norm1(self, g):
+        assert self.norm_capable() and self.e.norm1 == 0
+        self.keep.append(g)
+        self.e.norm1, self.e.norm1_g = _lib.NORM_LN, g.data_ptr()
+        self.desc['norm1'] = 1
+
+    def set_norm2(self, kind, g, out_ptr, ld, *, film_ptr=None, film_ld=0, rows_per_sample=0):
+        assert self.norm_capable() and self.e.norm2 == 0
+        self.keep.append(g)
+        e = self.e
+        e.norm2, e.norm2_g, e.out_norm, e.ld_norm = kind, g.data_ptr(), out_ptr, ld
+        e.film, e.film_ld, e.rows_per_sample = film_ptr, film_ld, rows_per_sample
+        self.desc['norm2'] = kind
 
     def __call__(self, stream):
         _lib.check(self.lib.b200_conv_gemm(*self.args, stream), 'b200_conv_gemm')

@@ -36,10 +36,11 @@ def _ceil(a, b):
 
 class Rows:
     """NHWC pixel rows: [rows, C] bf16 with row stride ld; (H, W) is the pixel grid per sample."""
-    __slots__ = ('t', 'C', 'ld', 'H', 'W')
+    __slots__ = ('t', 'C', 'ld', 'H', 'W', 'call')
 
     def __init__(self, t, C, H=1, W=1):
         self.t, self.C, self.ld, self.H, self.W = t, C, t.shape[-1], H, W
+        self.call = None      # the GemmCall that produces these rows (a later consumer may attach its pre-norm to that epilogue)
 
     @property
     def ptr(self):
@@ -145,6 +146,8 @@ class UnetPlan:
         self.text_hiddens = self._zeros((R, a.time_cond_dim), torch.float32)
         self._scratch = None
         self.sampler_state = {}      # persistent sampler buffers + captured step graphs (imagen.py / elucidated.py)
+        self.fuse_norm = os.environ.get('B200_IMAGEN_FUSE_NORM', '1') != '0'
+        self.n_fused = 0             # norms that run inside a GEMM epilogue instead of their own kernel
         self._build()
 
     # ------------------------------------------------------------------ small helpers
@@ -186,7 +189,7 @@ class UnetPlan:
             ksplit = self.lib.b200_conv_gemm_splitk(gB, gH, gW, N, ktot)
             nscratch = ksplit * M * npad if ksplit > 1 else 0
         call = ops.GemmCall(
-            [(s.ptr, s.C, s.ld) for s in srcs], segs, grid, wpacked, N, out if isinstance(out, int) else out.data_ptr(),
+            [(s.ptr, s.C, s.ld) for s in srcs], segs, grid, wpacked, N, out if (out is None or isinstance(out, int)) else out.data_ptr(),
             bias=self._wts.put(ops.padded_bias(bias, N, 'cpu')) if bias is not None else None,
             residual=residual.ptr if residual is not None else None, ldr=residual.ld if residual is not None else 0,
             out2_ptr=(out2 if isinstance(out2, int) else out2.data_ptr()) if out2 is not None else None,
@@ -195,14 +198,15 @@ class UnetPlan:
         call.desc['ksplit'] = ksplit
         self._keep.append(call)
         self._ops.append((call.lib.b200_conv_gemm, call.args, 'b200_conv_gemm'))
+        return call
 
-    def _linear(self, x: Rows, W, N, out: Rows = None, **epi):
-        """pixel-row linear layer y = x @ W^T (W: [N, C])."""
+    def _linear(self, x: Rows, W, N, out: Rows = None, out_raw=True, **epi):
+        """pixel-row linear layer y = x @ W^T (W: [N, C]).  out_raw=False: only the fused norm output (epi: norm2...) is stored."""
         M = x.rows
         if out is None:
             out = self._new(M, N, x.H, x.W)
         wp = self._pack([W], N)
-        self._gemm([x], [(0, 0, 0)], (1, 1, M), wp, N, out.t, ldc=out.ld, **epi)
+        out.call = self._gemm([x], [(0, 0, 0)], (1, 1, M), wp, N, out.t if out_raw else None, ldc=out.ld, **epi)
         return out
 
     def _conv_taps(self, k):
@@ -212,7 +216,45 @@ class UnetPlan:
         """k x k conv (pad k//2) over the channel concat of srcs; Wt: [N, sum C, k, k]; split = channel counts in Wt."""
         segs, mats = ops.conv_segments(Wt, split or [s.C for s in srcs])
         s0 = srcs[0]
-        self._gemm(srcs, segs, (self.R, s0.H, s0.W), self._pack(mats, N), N, out, **epi)
+        return self._gemm(srcs, segs, (self.R, s0.H, s0.W), self._pack(mats, N), N, out, **epi)
+
+    # ---- norm fusion (north star: "GroupNorm+SiLU and time-embed FiLM scale/shift fused into the preceding conv epilogue").
+    # Where one GEMM tile spans all channels (64 <= C <= 256) the per-pixel norm runs in the producing GEMM's epilogue
+    # (b200_epilogue.norm1 / norm2) instead of a separate HBM round trip.  B200_IMAGEN_FUSE_NORM=0 plans the stand-alone kernels.
+    def _fusable(self, C):
+        return self.fuse_norm and self.impl == _lib.IMPL_TCGEN05 and 64 <= C <= 256 and C % 32 == 0
+
+    def _attach_norm(self, x: Rows, kind, gt, **film):
+        """Try to let x's producer GEMM also emit norm(x): returns the normalised Rows or None."""
+        c = x.call
+        if c is None or not self._fusable(x.C) or not c.norm_capable() or c.e.norm2 != 0:
+            return None
+        out = self._new(x.rows, x.C, x.H, x.W)
+        c.set_norm2(kind, gt, out.ptr, out.ld, **film)
+        self.n_fused += 1
+        return out
+
+    def _prenorm_ln(self, x: Rows, g):
+        """LayerNorm(x) * g feeding a linear layer: fused into x's producer when possible, else the row kernel."""
+        out = self._attach_norm(x, _lib.NORM_LN, self._f32(g.flatten()))
+        return out if out is not None else self._layernorm(x, g)
+
+    def _rms_film_silu(self, srcs, gamma, din, skip, n, film_off=None):
+        """ChanRMSNorm -> [FiLM] -> SiLU over the channel concat of srcs (Block, imagen_pytorch.py:683-691)."""
+        gt = self._f32(gamma.flatten() * math.sqrt(din))
+        film = {}
+        if film_off is not None:
+            film = dict(film_ptr=self.film.data_ptr() + 4 * film_off, film_ld=self.film.shape[1], rows_per_sample=n)
+        if len(srcs) == 1:
+            out = self._attach_norm(srcs[0], _lib.NORM_RMS_FILM_SILU, gt, **film)
+            if out is not None:
+                return out
+        M = srcs[0].rows
+        out = self._new(M, din, srcs[0].H, srcs[0].W)
+        sa = (Src * len(srcs))(*[Src(s.ptr, s.C, s.ld) for s in srcs])
+        self._keep.append(sa)
+        self._add('b200_rmsnorm_film_silu', sa, len(srcs), skip, gt.data_ptr(), film.get('film_ptr'), film.get('film_ld', 0), n, out.ptr, out.ld, M)
+        return out
 
     def _layernorm(self, x: Rows, g, residual: Rows = None):
         out = self._new(x.rows, x.C, x.H, x.W)
@@ -230,24 +272,24 @@ class UnetPlan:
         M = R * n
         din = sum(s.C for s in srcs)
         skip = a.skip_scale if len(srcs) == 2 else 1.0
-        # block1: ChanRMSNorm -> SiLU -> conv3x3 (:683-691)
-        a1 = self._new(M, din, Hc, Wc)
-        g1 = self._f32(sd[p + '.block1.norm.gamma'].flatten() * math.sqrt(din))
-        sa = (Src * len(srcs))(*[Src(s.ptr, s.C, s.ld) for s in srcs])
-        self._keep.append(sa)
-        self._add('b200_rmsnorm_film_silu', sa, len(srcs), skip, g1.data_ptr(), None, 0, n, a1.ptr, a1.ld, M)
-        h = self._new(M, dout, Hc, Wc)
-        self._conv([a1], sd[p + '.block1.project.weight'], dout, h.t, ldc=h.ld, bias=sd[p + '.block1.project.bias'])
-        if cross_heads is not None:
-            h = self._cross_attention(p + '.cross_attn', h, cross_heads)
-        # block2: ChanRMSNorm -> FiLM(scale+1, shift) -> SiLU -> conv3x3
-        a2 = self._new(M, dout, Hc, Wc)
-        g2 = self._f32(sd[p + '.block2.norm.gamma'].flatten() * math.sqrt(dout))
-        film_off = self.film_offsets[p]
-        s2 = (Src * 1)(Src(h.ptr, h.C, h.ld))
-        self._keep.append(s2)
-        self._add('b200_rmsnorm_film_silu', s2, 1, 1.0, g2.data_ptr(), self.film.data_ptr() + 4 * film_off, self.film.shape[1], n,
-                  a2.ptr, a2.ld, M)
+        # block1: ChanRMSNorm -> SiLU -> conv3x3 (:683-691); block2: ChanRMSNorm -> FiLM(scale+1, shift) -> SiLU -> conv3x3.
+        # Both norms are emitted by the epilogue of the GEMM that produces their input when a tile spans all channels.
+        a1 = self._rms_film_silu(srcs, sd[p + '.block1.norm.gamma'], din, skip, n)
+        W1, b1 = sd[p + '.block1.project.weight'], sd[p + '.block1.project.bias']
+        g2, film_off = sd[p + '.block2.norm.gamma'], self.film_offsets[p]
+        if cross_heads is None and self._fusable(dout):
+            # conv1's epilogue writes a2 = SiLU(FiLM(RMSNorm(h))) directly; h itself is never stored
+            a2 = self._new(M, dout, Hc, Wc)
+            self._conv([a1], W1, dout, None, bias=b1, norm2=_lib.NORM_RMS_FILM_SILU, norm2_g=self._f32(g2.flatten() * math.sqrt(dout)),
+                       film_ptr=self.film.data_ptr() + 4 * film_off, film_ld=self.film.shape[1], rows_per_sample=n, out_norm_ptr=a2.ptr, ld_norm=a2.ld)
+            self.n_fused += 1
+        else:
+            h = self._new(M, dout, Hc, Wc)
+            h.call = self._conv([a1], W1, dout, h.t, ldc=h.ld, bias=b1)
+            if cross_heads is not None:
+                a2 = self._cross_attention(p + '.cross_attn', h, cross_heads, g2, film_off)
+            else:
+                a2 = self._rms_film_silu([h], g2, dout, 1.0, n, film_off)
         W2, b2 = sd[p + '.block2.project.weight'], sd[p + '.block2.project.bias']
         has_res = (p + '.res_conv.weight') in sd
         if has_res:
@@ -282,9 +324,9 @@ class UnetPlan:
                 segs.append((i + 1, 0, 0))
                 mats.append(Wr[:, o:o + s.C])
                 o += s.C
-            self._gemm([a2, *srcs], segs, (R, Hc, Wc), self._pack(mats, dout), dout, out.t, ldc=out.ld, bias=b2 + br)
+            out.call = self._gemm([a2, *srcs], segs, (R, Hc, Wc), self._pack(mats, dout), dout, out.t, ldc=out.ld, bias=b2 + br)
         else:
-            self._conv([a2], W2, dout, out.t, ldc=out.ld, bias=b2, residual=srcs[0])
+            out.call = self._conv([a2], W2, dout, out.t, ldc=out.ld, bias=b2, residual=srcs[0])
         return out
 
     def _gca(self, p, h: Rows):
@@ -311,12 +353,15 @@ class UnetPlan:
             return 0.0
         return float((self.sdc[p + '.q_scale'].abs() * self.sdc[p + '.k_scale'].abs()).max().item()) * 8.0 * LOG2E * 1.02
 
-    def _cross_attention(self, p, h: Rows, heads):
-        """CrossAttention.forward + residual (imagen_pytorch.py:793-834, :749)."""
+    def _cross_attention(self, p, h: Rows, heads, g2, film_off):
+        """CrossAttention.forward + residual (imagen_pytorch.py:793-834, :749), followed by block2's ChanRMSNorm -> FiLM -> SiLU
+        (:683-691): returns a2, the input of block2's conv.  When a GEMM tile spans all channels the pre-norm LayerNorm runs in the
+        epilogue of the conv that produced h, and to_out's epilogue does LayerNorm -> + h -> RMSNorm/FiLM/SiLU: 2 launches
+        (to_q, attention) + to_out instead of 5 + the block norm."""
         sd, R = self.sdc, self.R
         n, M, Cc = h.H * h.W, h.rows, h.C
         inner = heads * 64
-        hn = self._layernorm(h, sd[p + '.norm.g'])
+        hn = self._prenorm_ln(h, sd[p + '.norm.g'])
         qs = self._f32(sd[p + '.q_scale'] * (8.0 * LOG2E))
         q = self._linear(hn, sd[p + '.to_q.weight'], inner, l2_cols=inner, l2_scale=qs)
         nk = self.n_ctx + 1
@@ -332,8 +377,16 @@ class UnetPlan:
         o = self._new(M, inner, h.H, h.W)
         self._add('b200_attention', q.ptr, o.ptr, n * inner, 64, inner, n, Kc.data_ptr(), Vc.data_ptr(), nk * inner, 64, inner, nk, R, heads,
                   self._logit_bound(p))
+        if self._fusable(Cc):
+            a2 = self._new(M, Cc, h.H, h.W)
+            self._linear(o, sd[p + '.to_out.0.weight'], Cc, out=a2, out_raw=False, norm1=_lib.NORM_LN, norm1_g=self._f32(sd[p + '.to_out.1.g'].flatten()),
+                         residual=h, norm2=_lib.NORM_RMS_FILM_SILU, norm2_g=self._f32(g2.flatten() * math.sqrt(Cc)),
+                         film_ptr=self.film.data_ptr() + 4 * film_off, film_ld=self.film.shape[1], rows_per_sample=n, out_norm_ptr=a2.ptr, ld_norm=a2.ld)
+            self.n_fused += 2
+            return a2
         y = self._linear(o, sd[p + '.to_out.0.weight'], Cc)
-        return self._layernorm(y, sd[p + '.to_out.1.g'], residual=h)
+        h2 = self._layernorm(y, sd[p + '.to_out.1.g'], residual=h)
+        return self._rms_film_silu([h2], g2, Cc, 1.0, n, film_off)
 
     def _transformer(self, p, x: Rows, depth, has_ctx):
         """TransformerBlock.forward (imagen_pytorch.py:1012-1022): multi-query self-attention + feed-forward."""
@@ -342,7 +395,7 @@ class UnetPlan:
         heads, inner = a.heads, a.inner
         for l in range(depth):
             q_, ff = f'{p}.layers.{l}.0', f'{p}.layers.{l}.1'
-            xn = self._layernorm(x, sd[q_ + '.norm.g'])
+            xn = self._prenorm_ln(x, sd[q_ + '.norm.g'])
             qs = self._f32(sd[q_ + '.q_scale'] * (8.0 * LOG2E))
             q = self._linear(xn, sd[q_ + '.to_q.weight'], inner, l2_cols=inner, l2_scale=qs)
             npre = (self.n_ctx if has_ctx else 0) + 1
@@ -366,13 +419,27 @@ class UnetPlan:
             # all heads of a sample share K/V: heads*n query rows of width 64 form ONE attention problem
             self._add('b200_attention', q.ptr, o.ptr, n * inner, 0, 64, heads * n, Kb.data_ptr(), Vb.data_ptr(), Mtot * 64, 0, 64, Mtot, R, 1,
                       self._logit_bound(q_))
-            y = self._linear(o, sd[q_ + '.to_out.0.weight'], Cc)
-            x1 = self._layernorm(y, sd[q_ + '.to_out.1.g'], residual=x)
-            f = self._layernorm(x1, sd[ff + '.0.g'])
             hid = sd[ff + '.1.weight'].shape[0]
-            hdn = self._linear(f, sd[ff + '.1.weight'], hid, act=_lib.ACT_GELU)
-            hn = self._layernorm(hdn, sd[ff + '.3.g'])
-            x = self._linear(hn, sd[ff + '.4.weight'], Cc, residual=x1)
+            if self._fusable(Cc):
+                # to_out epilogue: LayerNorm -> + x (= x1) -> LayerNorm of the feed-forward (:1018-1020, :975): two outputs, no row kernels
+                x1, f = self._new(M, Cc, x.H, x.W), self._new(M, Cc, x.H, x.W)
+                self._linear(o, sd[q_ + '.to_out.0.weight'], Cc, out=x1, norm1=_lib.NORM_LN, norm1_g=self._f32(sd[q_ + '.to_out.1.g'].flatten()),
+                             residual=x, norm2=_lib.NORM_LN, norm2_g=self._f32(sd[ff + '.0.g'].flatten()), out_norm_ptr=f.ptr, ld_norm=f.ld)
+                self.n_fused += 2
+            else:
+                y = self._linear(o, sd[q_ + '.to_out.0.weight'], Cc)
+                x1 = self._layernorm(y, sd[q_ + '.to_out.1.g'], residual=x)
+                f = self._layernorm(x1, sd[ff + '.0.g'])
+            if self._fusable(hid):
+                # FF1 epilogue: GELU -> LayerNorm over the hidden width (:976-978); only the normalised tensor is stored
+                hn = self._new(M, hid, x.H, x.W)
+                self._linear(f, sd[ff + '.1.weight'], hid, out=hn, out_raw=False, act=_lib.ACT_GELU, norm2=_lib.NORM_LN,
+                             norm2_g=self._f32(sd[ff + '.3.g'].flatten()), out_norm_ptr=hn.ptr, ld_norm=hn.ld)
+                self.n_fused += 1
+            else:
+                hdn = self._linear(f, sd[ff + '.1.weight'], hid, act=_lib.ACT_GELU)
+                hn = self._layernorm(hdn, sd[ff + '.3.g'])
+            x = self._linear(hn, sd[ff + '.4.weight'], Cc, residual=x1)     # x.call: the next layer's pre-norm attaches here
         return x
 
     def _downsample(self, p, x: Rows, dout):

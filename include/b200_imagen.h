@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 typedef enum {
   B200_OK = 0,
@@ -105,6 +105,25 @@ typedef struct {
   int32_t ps_C;           /* C' for B200_OUT_PIXEL_SHUFFLE */
   /* also store rows at +dup_rows (classifier-free-guidance batch duplication); 0 = off */
   int32_t dup_rows;
+  /* ---- per-row normalisations fused into the epilogue (ABI v2).  Available when one N tile spans all channels
+   *      (64 <= N <= 256, N % 32 == 0), out_mode == B200_OUT_BF16 and none of split_col / rows_per_group / l2_cols / dup_rows:
+   *        v  = act(acc + bias) * out_scale
+   *        v  = norm1 ? LayerNorm(v) * norm1_g : v                     (custom gain-only LayerNorm, eps 1e-5, imagen_pytorch.py:331-349)
+   *        w  = v + residual                                           -> out (bf16; may be NULL when only out_norm is wanted)
+   *        y  = norm2 == 1 ? LayerNorm(w) * norm2_g                    (the next pre-norm: imagen_pytorch.py:516, :775, :975)
+   *           : norm2 == 2 ? SiLU( w / |w|_2 * norm2_g [* (scale+1) + shift] )   (Block: ChanRMSNorm -> FiLM -> SiLU, :683-691;
+   *                          norm2_g = gamma * sqrt(N) folded by the caller)
+   *        y -> out_norm (bf16)
+   *      Statistics are taken on the fp32 values (the reference's arithmetic), not on bf16-rounded ones. */
+  int32_t norm1;
+  const float* norm1_g;     /* [N] */
+  int32_t norm2;
+  const float* norm2_g;     /* [N] */
+  const float* film;        /* norm2 == 2: fp32 rows [scale (N) | shift (N)] per sample, row pitch film_ld; NULL = no FiLM */
+  int32_t film_ld;
+  int32_t rows_per_sample;  /* output rows per sample (selects the film row) */
+  void* out_norm;
+  int32_t ld_norm;
 } b200_epilogue;
 
 /* Packed weight layout: bf16 [Npad, Ktot], Npad = N rounded up to the N tile, K ordered by

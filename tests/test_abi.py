@@ -28,7 +28,7 @@ def test_python_binding_covers_the_header():
 
 def test_abi_version_and_npad_without_gpu():
     lib = _lib.load()
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
     assert [_lib.npad(n) for n in (3, 32, 33, 64, 65, 128, 129, 512)] == [32, 32, 64, 64, 128, 128, 256, 512]
     assert lib.b200_gca_nchunk(64) == 1 and lib.b200_gca_nchunk(4096) == 16
 

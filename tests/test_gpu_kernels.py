@@ -192,6 +192,71 @@ def test_qk_l2norm_and_kv_scatter_epilogues(impl):
     assert Kb[:, :npre].abs().max() == 0                              # prefix rows untouched
 
 
+# ------------------------------------------------------------------------------------------------ norms fused into the GEMM epilogue
+
+def _ln_ref(x, g):
+    mean, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
+    return (x - mean) * (var + 1e-5).rsqrt() * g
+
+
+@pytest.mark.parametrize('case', ['conv3x3_rms_film_only', 'linear_ln_res_ln', 'linear_ln_res_rms_film_only', 'linear_gelu_ln_only', 'conv_res_ln_lazy',
+                                  'n64_rms', 'n192_ln_res_rms', 'n256_ln_res_ln', 'ragged_rows_rms'])
+def test_gemm_epilogue_fused_norms(case):
+    """b200_epilogue.norm1 / norm2 (ABI v2): LayerNorm -> + residual -> {LayerNorm | RMSNorm+FiLM+SiLU} inside the tcgen05 GEMM epilogue
+    against the same chain in torch fp32 on the bf16-rounded operands (imagen_pytorch.py:331-349, :322-329, :683-691)."""
+    cfg = {
+        'conv3x3_rms_film_only': dict(B=2, H=16, W=16, C=128, N=128, k=3, n1=False, res=False, n2=2, film=True, raw=False, act=0),
+        'linear_ln_res_ln': dict(B=1, H=1, W=777, C=512, N=128, k=1, n1=True, res=True, n2=1, film=False, raw=True, act=0),
+        'linear_ln_res_rms_film_only': dict(B=2, H=8, W=8, C=512, N=128, k=1, n1=True, res=True, n2=2, film=True, raw=False, act=0),
+        'linear_gelu_ln_only': dict(B=1, H=1, W=1000, C=128, N=256, k=1, n1=False, res=False, n2=1, film=False, raw=False, act=_lib.ACT_GELU),
+        'conv_res_ln_lazy': dict(B=3, H=8, W=8, C=64, N=128, k=3, n1=False, res=True, n2=1, film=False, raw=True, act=0),
+        'n64_rms': dict(B=2, H=8, W=8, C=64, N=64, k=3, n1=False, res=False, n2=2, film=True, raw=True, act=0),
+        'n192_ln_res_rms': dict(B=2, H=8, W=8, C=192, N=192, k=1, n1=True, res=True, n2=2, film=False, raw=True, act=0),
+        'n256_ln_res_ln': dict(B=1, H=16, W=16, C=256, N=256, k=3, n1=True, res=True, n2=1, film=False, raw=True, act=0),
+        'ragged_rows_rms': dict(B=3, H=5, W=7, C=128, N=128, k=3, n1=False, res=True, n2=2, film=True, raw=True, act=0),
+    }[case]
+    B, H, W, Cin, N, k = (cfg[x] for x in ('B', 'H', 'W', 'C', 'N', 'k'))
+    M = B * H * W
+    x = rnd(B, H, W, Cin, seed=1).to(BF16)
+    Wt = rnd(N, Cin, k, k, scale=1.0 / math.sqrt(Cin * k * k), seed=2)
+    bias = rnd(N, scale=0.1, seed=3)
+    res = (rnd(M, N, seed=4) * 1.5 + 0.3).to(BF16) if cfg['res'] else None
+    g1 = (1 + 0.2 * rnd(N, seed=5)).contiguous()
+    g2 = (1 + 0.2 * rnd(N, seed=6)).contiguous()
+    film = rnd(B, 2 * N + 8, scale=0.3, seed=7).contiguous() if cfg['film'] else None    # [scale | shift] rows with a row pitch > 2N
+    out = torch.zeros(M, N, dtype=BF16, device=DEV) if cfg['raw'] else None
+    out_n = torch.zeros(M, N, dtype=BF16, device=DEV)
+    segs, mats = ops.conv_segments(Wt, [Cin])
+    call = ops.GemmCall([(x.data_ptr(), Cin, Cin)], segs, (B, H, W), ops.pack_weight(mats, N, DEV), N, out.data_ptr() if out is not None else None,
+                        bias=ops.padded_bias(bias, N, DEV), act=cfg['act'], residual=res.data_ptr() if res is not None else None, ldr=N, ldc=N)
+    assert call.norm_capable()
+    if cfg['n1']:
+        call.set_norm1(g1)
+    g2k = g2 * math.sqrt(N) if cfg['n2'] == 2 else g2            # the caller folds sqrt(C) into the RMS gamma
+    call.set_norm2(cfg['n2'], g2k.contiguous(), out_n.data_ptr(), N, film_ptr=film.data_ptr() if film is not None else None,
+                   film_ld=film.shape[1] if film is not None else 0, rows_per_sample=H * W)
+    call(stream())
+    torch.cuda.synchronize()
+    # torch fp32 reference
+    v = F.conv2d(x.float().permute(0, 3, 1, 2), Wt.to(BF16).float(), bias, padding=k // 2).permute(0, 2, 3, 1).reshape(M, N)
+    if cfg['act'] == _lib.ACT_GELU:
+        v = F.gelu(v)
+    if cfg['n1']:
+        v = _ln_ref(v, g1)
+    w = v + (res.float() if res is not None else 0.)
+    if cfg['n2'] == 1:
+        y = _ln_ref(w, g2)
+    else:
+        y = F.normalize(w, dim=-1) * g2 * math.sqrt(N)
+        if film is not None:
+            fr = film.repeat_interleave(H * W, dim=0)
+            y = y * (fr[:, :N] + 1) + fr[:, N:2 * N]
+        y = F.silu(y)
+    if out is not None:
+        assert_close(out, w, 1.2e-2, 1.5e-2, f'{case}: raw')
+    assert_close(out_n, y, 1.2e-2, 1.5e-2, f'{case}: normalised')
+
+
 # ------------------------------------------------------------------------------------------------ attention
 
 def ref_attention(q, k, v):

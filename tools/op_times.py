@@ -28,7 +28,7 @@ for n, t in zip(names, med):
     if n == 'b200_conv_gemm':
         d = next(gd)
         M = d['B'] * d['H'] * d['W']
-        key = f"gemm {'conv' if d['nseg'] > 1 else 'lin '} M={M} N={d['N']} K={d['K']}"
+        key = f"gemm {'conv' if d['nseg'] > 1 else 'lin '} M={M} N={d['N']} K={d['K']}" + (f" norm{d.get('norm1', 0)}{d.get('norm2', 0)}" if d.get('norm1') or d.get('norm2') else '')
     agg[key][0] += 1
     agg[key][1] += t
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
