@@ -74,6 +74,7 @@ SIGNATURES = {
     'b200_gate_residual': [_P, _I, _P, _P, _I, _P, _I, _L, _I, _I, _P],
     'b200_im2col_init': [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     'b200_im2col_init3': [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    'b200_im2col_init4': [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     'b200_pixel_unshuffle': [_P, _I, _I, _I, _I, _I, _P, _P],
     'b200_nchw_to_rows': [_P, _I, _I, _I, _I, _P, _I, _P],
     'b200_make_time_cond': [_P, _P, _P, _I, _I, _P, _P],

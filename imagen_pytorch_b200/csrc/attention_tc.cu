@@ -28,7 +28,7 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_DEFAULT_VARIANT = 12;   // ping-pong with 16 softmax warps (profiles/r01_attention_variant_sweep.txt)
+constexpr int FA_DEFAULT_VARIANT = 20;   // ping-pong, P in tensor memory, 16 softmax warps (profiles/r02_attention_variant_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
@@ -540,7 +540,11 @@ constexpr int PT_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 256 + 
 template <int POLY>
 __device__ __forceinline__ bool pt_use_poly(int idx) { return POLY > 0 && (idx % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1; }
 
-template <int POLY, int SUB>   // POLY: every POLY-th exponential on the FMA pipe (0 = all MUFU); SUB: softmax warps per lane quarter per group
+// ORDER: the two groups take turns on the MUFU pipe (token passed through order_bar).  Without it the two identical periodic
+// softmax pipelines lock IN phase: both exponentiate at the same time at half speed each, then both wait for their next S tile with
+// the MUFU pipe idle (measured: XU pipe 62% busy at 16/clk/SM peak).  With the token, group B's TMEM reads / barrier round trips /
+// S MMA latency run under group A's exponentials and vice versa.
+template <int POLY, int SUB, bool ORDER>   // POLY: every POLY-th exponential on the FMA pipe (0 = all MUFU); SUB: softmax warps per lane quarter per group
 __global__ void __launch_bounds__(128 + 256 * SUB, 1)
 flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
@@ -557,9 +561,10 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* p_full = s_empty + 2;                       // [group][half]
   uint64_t* p_empty = p_full + 4;                       // [group][half]
   uint64_t* o_full = p_empty + 4;                       // [group]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* order_bar = o_full + 2;                     // [group]: group g may start exponentiating its next tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(order_bar + 2);
   float* sL = reinterpret_cast<float*>(bars + 32);      // [group][sub][128] partial row sums
-  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 1 <= 32, "barrier block is 256 bytes");
+  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 2 + 1 <= 32, "barrier block is 256 bytes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * (2 * FA_BM);
@@ -578,6 +583,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       mbar_init(&s_full[g], 1);
       mbar_init(&s_empty[g], 128 * SUB);
       mbar_init(&o_full[g], 1);
+      mbar_init(&order_bar[g], 4 * SUB);                // one arrival per softmax warp of the OTHER group
       for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }
     }
     fence_barrier_init();
@@ -667,9 +673,19 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const int key0 = j * FA_BN;
       const bool ragged = key0 + FA_BN > p.n_keys;
       const bool last_dead = dead1 && j == ntiles - 1;
-      if (SUB == 2 && sub == 1 && last_dead) break;     // nothing valid in this warp's half of the last tile
+      // token: A(j) follows B(j-1), B(j) follows A(j); a fresh barrier passes A's first wait (parity trick of the empty barriers)
+      const uint32_t tok_par = g == 0 ? (uint32_t)((j & 1) ^ 1) : (uint32_t)(j & 1);
+      if (SUB == 2 && sub == 1 && last_dead) {          // nothing valid in this warp's half of the last tile: only pass the token on
+        if (ORDER) {
+          mbar_wait(&order_bar[g], tok_par);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&order_bar[g ^ 1]);
+        }
+        break;
+      }
       mbar_wait(&s_full[g], (uint32_t)(j & 1));
       tc_fence_after();
+      bool have_token = !ORDER;
       constexpr int CH = SUB == 2 ? 32 : 64;
 #pragma unroll 1
       for (int hh = 0; hh < 2 / SUB; ++hh) {
@@ -693,6 +709,10 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half of P
             tc_fence_after();
           }
+          if (!have_token) {                    // scores are in registers: now wait for this group's turn on the MUFU pipe
+            mbar_wait(&order_bar[g], tok_par);
+            have_token = true;
+          }
 #pragma unroll
           for (int t = 0; t < CH / 32; ++t) {
             uint32_t pk[16];
@@ -711,6 +731,10 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             }
             tmem_st16(p_col + (uint32_t)((c0 + 32 * t) >> 1), pk);
           }
+        }
+        if (ORDER && (SUB == 2 || hh == 1 || last_dead)) {   // exponentials of this tile issued: the other group's turn
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&order_bar[g ^ 1]);
         }
         tmem_st_wait();                          // the stores have landed in tensor memory ...
         tc_fence_before();                       // ... and are ordered before the issuer's MMAs through the barrier
@@ -832,21 +856,24 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
     case 12: PP_LAUNCH(0, 2); break;   // ping-pong, 16 softmax warps (column halves)
     case 13: PP_LAUNCH(4, 2); break;   // ... + 1/4 polynomial exp2
-#define PT_LAUNCH(POLY, SUB)                                                                                                     \
+#define PT_LAUNCH(POLY, SUB, ORDER)                                                                                              \
   {                                                                                                                                \
-    B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB>), PT_SMEM);                                                                  \
+    B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB, ORDER>), PT_SMEM);                                                           \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
-    flash_attn_pt_kernel<POLY, SUB><<<grid2, 128 + 256 * SUB, PT_SMEM, st>>>(mq, mk, mv, p);                                      \
+    flash_attn_pt_kernel<POLY, SUB, ORDER><<<grid2, 128 + 256 * SUB, PT_SMEM, st>>>(mq, mk, mv, p);                               \
   }
-    case 20: PT_LAUNCH(0, 2); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
-    case 21: PT_LAUNCH(8, 2); break;   // ... + 1/8 of the exponentials on the FMA pipe
-    case 22: PT_LAUNCH(5, 2); break;   // ... + 1/5
-    case 23: PT_LAUNCH(4, 2); break;   // ... + 1/4
-    case 24: PT_LAUNCH(3, 2); break;   // ... + 1/3
-    case 25: PT_LAUNCH(2, 2); break;   // ... + 1/2
-    case 26: PT_LAUNCH(0, 1); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
-    case 27: PT_LAUNCH(4, 1); break;
-    case 28: PT_LAUNCH(3, 1); break;
+    case 20: PT_LAUNCH(0, 2, false); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
+    case 21: PT_LAUNCH(8, 2, false); break;   // ... + 1/8 of the exponentials on the FMA pipe
+    case 23: PT_LAUNCH(4, 2, false); break;   // ... + 1/4
+    case 26: PT_LAUNCH(0, 1, false); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
+    case 27: PT_LAUNCH(4, 1, false); break;
+    case 30: PT_LAUNCH(0, 2, true); break;    // + MUFU token between the two groups
+    case 31: PT_LAUNCH(8, 2, true); break;
+    case 32: PT_LAUNCH(5, 2, true); break;
+    case 33: PT_LAUNCH(4, 2, true); break;
+    case 34: PT_LAUNCH(3, 2, true); break;
+    case 36: PT_LAUNCH(0, 1, true); break;
+    case 37: PT_LAUNCH(4, 1, true); break;
 #undef PT_LAUNCH
     default: PP_LAUNCH(0, 1); break;   // ping-pong: two query tiles per CTA, all exponentials on MUFU
 #undef PP_LAUNCH

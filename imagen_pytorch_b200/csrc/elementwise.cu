@@ -358,11 +358,11 @@ __global__ void gate_residual_kernel(const __nv_bfloat16* __restrict__ x, int ld
 constexpr int IM2COL_ROWS = 32;
 
 __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restrict__ img0, int C0, const float* __restrict__ img1, int C1,
-                                                          const float* __restrict__ img2, int C2, int B, int H, int W, int ks,
-                                                          __nv_bfloat16* __restrict__ out, int Kpad) {
+                                                          const float* __restrict__ img2, int C2, const float* __restrict__ img3, int C3, int B, int H,
+                                                          int W, int ks, __nv_bfloat16* __restrict__ out, int Kpad) {
   // k -> (dy, dx, channel) decode table, built once per block instead of a div/mod chain per element
   extern __shared__ int lut[];
-  const int Cin = C0 + C1 + C2, pad = ks / 2, K = ks * ks * Cin;
+  const int Cin = C0 + C1 + C2 + C3, pad = ks / 2, K = ks * ks * Cin;
   for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
     int v = -1;
     if (k < K) {
@@ -394,7 +394,8 @@ __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restric
         if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
           v = c < C0 ? __ldg(img0 + (((long long)b * C0 + c) * H + hh) * W + ww)
               : c < C0 + C1 ? __ldg(img1 + (((long long)b * C1 + (c - C0)) * H + hh) * W + ww)
-                            : __ldg(img2 + (((long long)b * C2 + (c - C0 - C1)) * H + hh) * W + ww);
+              : c < C0 + C1 + C2 ? __ldg(img2 + (((long long)b * C2 + (c - C0 - C1)) * H + hh) * W + ww)
+                                 : __ldg(img3 + (((long long)b * C3 + (c - C0 - C1 - C2)) * H + hh) * W + ww);
         }
       }
       f[j] = v;
@@ -566,16 +567,21 @@ extern "C" int b200_gate_residual(const void* x, int32_t ldx, const float* gate,
   return B200_OK;
 }
 
-extern "C" int b200_im2col_init3(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2, int B, int H, int W, int ksize,
-                                 void* out, int32_t Kpad, void* stream) {
+extern "C" int b200_im2col_init4(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2, const float* img3, int C3, int B,
+                                 int H, int W, int ksize, void* out, int32_t Kpad, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1) && (C2 == 0 || img2), "im2col: null pointer");
-  B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1 + C2), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
-  B200_REQUIRE(Kpad * 4 <= 48 * 1024 && C0 + C1 + C2 < 256, "im2col: patch too large");
+  B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1) && (C2 == 0 || img2) && (C3 == 0 || img3), "im2col: null pointer");
+  B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1 + C2 + C3), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
+  B200_REQUIRE(Kpad * 4 <= 48 * 1024 && C0 + C1 + C2 + C3 < 256, "im2col: patch too large");
   im2col_init_kernel<<<(unsigned)ceil_div64((long long)B * H * W, IM2COL_ROWS), 256, Kpad * sizeof(int), st>>>(
-      img0, C0, img1, C1, img2, C2, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
+      img0, C0, img1, C1, img2, C2, img3, C3, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
   B200_LAUNCH_OK();
   return B200_OK;
+}
+
+extern "C" int b200_im2col_init3(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2, int B, int H, int W, int ksize,
+                                 void* out, int32_t Kpad, void* stream) {
+  return b200_im2col_init4(img0, C0, img1, C1, img2, C2, nullptr, 0, B, H, W, ksize, out, Kpad, stream);
 }
 
 extern "C" int b200_im2col_init(const float* img0, int C0, const float* img1, int C1, int B, int H, int W, int ksize, void* out, int32_t Kpad,

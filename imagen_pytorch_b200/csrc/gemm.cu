@@ -573,10 +573,13 @@ __device__ __forceinline__ void flush32_to(__nv_bfloat16* base, int ld, const Ge
   __syncwarp();
 }
 
-template <int BNH, int HALVES, class Load32, class Wait32>
+// One epilogue warp owns 64 columns of its 32 rows and keeps them in registers: ONE pass over TMEM (the accumulator stage is handed
+// back to the MMA warp right after it), every value computed once (a first version re-read TMEM and recomputed bias / GELU /
+// norm1 for each statistics pass: 2-3x the instructions, and with 8 epilogue warps the fused GEMMs became instruction bound --
+// FF1+GELU+LN 102 us vs 45 + 25 us unfused).
+template <int HALVES, class Load32, class Wait32, class Release>
 __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo& ri, int n0, uint32_t stage, uint32_t meta, float2* xch, int parity,
-                                              int q, int half, int lane, Load32 load32, Wait32 wait32) {
-  static_assert(BNH % 32 == 0, "32-column passes");
+                                              int q, int half, int lane, Load32 load32, Wait32 wait32, Release release) {
   const EpiDev& e = p.epi;
   const int r = q * 32 + lane;
   const float invN = 1.f / (float)p.N;
@@ -593,105 +596,105 @@ __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo
     }
     return s;
   };
-  float va[32];
-  auto base = [&](int c) {                  // v = act(acc + bias) * out_scale of columns [n0 + c, +32)
-    load32(c, va);
-    wait32(va);
-    epi_math32(e, n0 + c, va);
-  };
-  float mean1 = 0.f, rstd1 = 1.f;
+  // ---- accumulator -> registers (columns >= N stay zero and are excluded from every statistic)
+  const bool h0 = n0 < p.N, h1 = n0 + 32 < p.N;
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) v[j] = 0.f;
+  if (h0) { load32(0, v); wait32(v); }
+  if (h1) { load32(32, v + 32); wait32(v + 32); }
+  release();                                // the MMA warp may overwrite this accumulator stage
+  if (h0) epi_math32(e, n0, v);
+  if (h1) epi_math32(e, n0 + 32, v + 32);
+  // ---- norm1: two-pass LayerNorm on the fp32 values
   if (e.norm1) {
     float s = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BNH; c += 32) {
-      if (n0 + c >= p.N) break;
-      base(c);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s += va[j];
-    }
-    mean1 = exchange(0, s, 0.f).x * invN;
+    for (int j = 0; j < 64; ++j) s += v[j];
+    const float mean = exchange(0, s, 0.f).x * invN;
     float vs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BNH; c += 32) {
-      if (n0 + c >= p.N) break;
-      base(c);
+    if (h0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { const float d = va[j] - mean1; vs += d * d; }
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; vs += d * d; }
     }
-    rstd1 = rsqrtf(exchange(1, vs, 0.f).x * invN + 1e-5f);
+    if (h1) {
+#pragma unroll
+      for (int j = 32; j < 64; ++j) { const float d = v[j] - mean; vs += d * d; }
+    }
+    const float rstd = rsqrtf(exchange(1, vs, 0.f).x * invN + 1e-5f);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (hh == 0 ? h0 : h1) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm1_g + n0 + 32 * hh + j));
+          float* w = v + 32 * hh + j;
+          w[0] = (w[0] - mean) * rstd * g4.x; w[1] = (w[1] - mean) * rstd * g4.y;
+          w[2] = (w[2] - mean) * rstd * g4.z; w[3] = (w[3] - mean) * rstd * g4.w;
+        }
+      }
+    }
   }
-  const __nv_bfloat16* rrow = (e.residual != nullptr && ri.valid) ? e.residual + ri.row * (long long)e.ldr : nullptr;
-  auto wval = [&](int c) {                  // w = norm1(v) + residual
-    base(c);
-    const int n = n0 + c;
-    if (e.norm1) {
+  // ---- residual (the thread's own row: 64-byte pieces)
+  if (e.residual != nullptr && ri.valid) {
+    const __nv_bfloat16* rrow = e.residual + ri.row * (long long)e.ldr + n0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm1_g + n + j));
-        va[j] = (va[j] - mean1) * rstd1 * g4.x; va[j + 1] = (va[j + 1] - mean1) * rstd1 * g4.y;
-        va[j + 2] = (va[j + 2] - mean1) * rstd1 * g4.z; va[j + 3] = (va[j + 3] - mean1) * rstd1 * g4.w;
+    for (int hh = 0; hh < 2; ++hh) {
+      if (hh == 0 ? h0 : h1) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(rrow + 32 * hh + j), f);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[32 * hh + j + t] += f[t];
+        }
       }
     }
-    if (rrow != nullptr) {
+  }
+  if (e.out != nullptr) {
+    if (h0) { stage32(v, stage, lane); flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n0, stage, meta, lane); }
+    if (h1) { stage32(v + 32, stage, lane); flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n0 + 32, stage, meta, lane); }
+  }
+  if (!e.norm2) return;
+  // ---- norm2 on w (fp32): LayerNorm (var = E[w^2] - mean^2) or RMSNorm -> FiLM -> SiLU
+  float s = 0.f, ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(rrow + n + j), f);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) va[j + t] += f[t];
-      }
-    }
-  };
-  float m2 = 0.f, k2 = 1.f;
-  if (e.norm2) {
-    float s = 0.f, ss = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BNH; c += 32) {
-      if (n0 + c >= p.N) break;
-      wval(c);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { s += va[j]; ss += va[j] * va[j]; }
-    }
-    const float2 t = exchange(2, s, ss);
-    if (e.norm2 == 1) {
-      m2 = t.x * invN;
-      k2 = rsqrtf(fmaxf(t.y * invN - m2 * m2, 0.f) + 1e-5f);
-    } else {
-      k2 = 1.f / fmaxf(sqrtf(t.y), 1e-12f);
-    }
+  for (int j = 0; j < 64; ++j) { s += v[j]; ss += v[j] * v[j]; }
+  const float2 t = exchange(2, s, ss);
+  float m2 = 0.f, k2;
+  if (e.norm2 == 1) {
+    m2 = t.x * invN;
+    k2 = rsqrtf(fmaxf(t.y * invN - m2 * m2, 0.f) + 1e-5f);
+  } else {
+    k2 = 1.f / fmaxf(sqrtf(t.y), 1e-12f);
   }
   const float* film = nullptr;
-  if (e.norm2 == 2 && e.film != nullptr) film = e.film + (long long)((unsigned)ri.row / (unsigned)e.rows_per_sample) * e.film_ld;
-#pragma unroll 1
-  for (int c = 0; c < BNH; c += 32) {
-    const int n = n0 + c;
-    if (n >= p.N) break;
-    wval(c);
-    if (e.out != nullptr) {
-      stage32(va, stage, lane);
-      flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n, stage, meta, lane);
-    }
-    if (e.norm2) {
+  if (e.norm2 == 2 && e.film != nullptr && ri.valid) film = e.film + (long long)((unsigned)ri.row / (unsigned)e.rows_per_sample) * e.film_ld;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    if (hh == 0 ? h0 : h1) {
+      float* w = v + 32 * hh;
+      const int n = n0 + 32 * hh;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm2_g + n + j));
-        va[j] = (va[j] - m2) * k2 * g4.x; va[j + 1] = (va[j + 1] - m2) * k2 * g4.y;
-        va[j + 2] = (va[j + 2] - m2) * k2 * g4.z; va[j + 3] = (va[j + 3] - m2) * k2 * g4.w;
+        w[j] = (w[j] - m2) * k2 * g4.x; w[j + 1] = (w[j + 1] - m2) * k2 * g4.y;
+        w[j + 2] = (w[j + 2] - m2) * k2 * g4.z; w[j + 3] = (w[j + 3] - m2) * k2 * g4.w;
       }
       if (e.norm2 == 2) {
-        if (film != nullptr && ri.valid) {
+        if (film != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(film + n + j));
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(film + p.N + n + j));
-            va[j] = va[j] * (s4.x + 1.f) + b4.x; va[j + 1] = va[j + 1] * (s4.y + 1.f) + b4.y;
-            va[j + 2] = va[j + 2] * (s4.z + 1.f) + b4.z; va[j + 3] = va[j + 3] * (s4.w + 1.f) + b4.w;
+            w[j] = w[j] * (s4.x + 1.f) + b4.x; w[j + 1] = w[j + 1] * (s4.y + 1.f) + b4.y;
+            w[j + 2] = w[j + 2] * (s4.z + 1.f) + b4.z; w[j + 3] = w[j + 3] * (s4.w + 1.f) + b4.w;
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) va[j] = silu_f(va[j]);
+        for (int j = 0; j < 32; ++j) w[j] = silu_f(w[j]);
       }
-      stage32(va, stage, lane);
+      stage32(w, stage, lane);
       flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out_norm), e.ld_norm, p, ri, n, stage, meta, lane);
     }
   }
@@ -842,12 +845,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
       if (!(p.debug & 1)) {
         if constexpr (NORM) {
-          static_assert(STAGED, "the norm epilogue stores through the staging tiles");
+          static_assert(STAGED && BNH == 64, "the norm epilogue keeps 64 columns per warp in registers and stores through the staging tiles");
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
           float2* xch = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 1024 + NEPI * EPI_STAGE_BYTES);
-          epilogue_norm<BNH, HALVES>(p, ri, n0 + half * BNH, stg, stg + 2048u, xch, tile_parity, q, half, lane,
-                                     [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
-                                     [&](float* v) { tmem_wait_regs32(v); });
+          epilogue_norm<HALVES>(p, ri, n0 + half * BNH, stg, stg + 2048u, xch, tile_parity, q, half, lane,
+                                [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                                [&](float* v) { tmem_wait_regs32(v); },
+                                [&]() {
+                                  tc_fence_before();
+                                  __syncwarp();
+                                  if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                                });
         } else if constexpr (STAGED) {
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
           epilogue_staged<BNH, (NEPI <= 8)>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
@@ -858,9 +866,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                    [&](float* v) { tmem_wait_regs16(v); });
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (!(NORM && !(p.debug & 1))) {      // (the norm epilogue released the accumulator itself, right after reading it)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -1434,7 +1444,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
     switch (BN) {
       case 64: return launch_tc2<64, 8, true, 4, true>(maps, mapB, mapO, p, ntiles, st);
       case 128: return launch_tc2<128, 5, true, 8, true>(maps, mapB, mapO, p, ntiles, st);
-      default: return launch_tc2<256, 4, true, 8, true>(maps, mapB, mapO, p, ntiles, st);
+      default: return launch_tc2<256, 3, true, 16, true>(maps, mapB, mapO, p, ntiles, st);
     }
   }
   if (pair) return BN == 256 ? launch_pair<256, 6>(maps, mapB, mapO, p, ntiles, st) : launch_pair<128, 8>(maps, mapB, mapO, p, ntiles, st);

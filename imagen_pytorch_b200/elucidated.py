@@ -86,7 +86,7 @@ class ElucidatedImagen(_SamplerBase):
     def one_unet_sample(self, unet, shape, *, unet_number, clamp=True, dynamic_threshold=True, cond_scale=1., use_tqdm=True,
                         inpaint_videos=None, inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5, init_images=None,
                         skip_steps=None, sigma_min=None, sigma_max=None, text_embeds=None, text_mask=None, lowres_cond_img=None,
-                        lowres_noise_times=None, **unsupported):
+                        lowres_noise_times=None, cond_images=None, **unsupported):
         inpaint_images = default(inpaint_videos, inpaint_images)
         for name, val in unsupported.items():
             if exists(val):
@@ -107,7 +107,7 @@ class ElucidatedImagen(_SamplerBase):
             keep = torch.cat((torch.ones(B, dtype=torch.bool, device=device), torch.zeros(R - B, dtype=torch.bool, device=device)))
             # NOTE: the reference hands the RAW low-res noise level to the U-Net here, not its log-SNR (:700, :727-728)
             plan.prepare(times, text_embeds=text_embeds, text_mask=text_mask, keep=keep, lowres_cond_img=lowres_cond_img,
-                         lowres_noise_times=lowres_noise_times)
+                         lowres_noise_times=lowres_noise_times, cond_images=cond_images)
             chw = Cimg * H * W
             q_lo, q_hi, q_w = quantile_ranks(chw, self.dynamic_thresholding_percentile, device)
             st_ = plan.sampler_state.setdefault('edm', {})
@@ -231,7 +231,10 @@ class ElucidatedImagen(_SamplerBase):
         try:
             device = default(device, self.device)
             self.reset_unets_all_one_device(device=device)
-            self._check_sample_args(texts, text_embeds, text_masks, dict(cond_images=cond_images, cond_video_frames=cond_video_frames,
+            if exists(cond_images) and cond_images.dtype == torch.uint8:      # cast_uint8_images_to_float (elucidated_imagen.py:581)
+                cond_images = cond_images / 255
+            self._check_cond_images(cond_images, start_at_unet_number, stop_at_unet_number)
+            self._check_sample_args(texts, text_embeds, text_masks, dict(cond_video_frames=cond_video_frames,
                                     post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos, video_frames=video_frames))
             if return_pil_images:
                 raise NotImplementedError('return_pil_images: convert the returned tensor yourself')
@@ -276,7 +279,7 @@ class ElucidatedImagen(_SamplerBase):
                                            skip_steps=unet_skip_steps,
                                            sigma_min=unet_sigma_min, sigma_max=unet_sigma_max, cond_scale=unet_cond_scale,
                                            lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
-                                           dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm)
+                                           dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm, cond_images=cond_images)
                 launches += self.last_launch_count
                 outputs.append(img)
                 if exists(stop_at_unet_number) and stop_at_unet_number == unet_number:

@@ -226,6 +226,14 @@ class _SamplerBase(nn.Module):
         assert not (exists(text_embeds) and text_embeds.shape[-1] != self.text_embed_dim), \
             f'invalid text embedding dimension being passed in (should be {self.text_embed_dim})'
 
+    def _check_cond_images(self, cond_images, start_at_unet_number=1, stop_at_unet_number=None):
+        """Unet.forward's check (imagen_pytorch.py:1555), raised before any device work."""
+        for i, unet in enumerate(self.unets, 1):
+            if i < start_at_unet_number or (exists(stop_at_unet_number) and i > stop_at_unet_number) or isinstance(unet, NullUnet):
+                continue
+            assert not (unet.has_cond_image ^ exists(cond_images)), \
+                'you either requested to condition on an image on the unet, but the conditioning image is not supplied, or vice versa'
+
     def _lowres_conditioning(self, img, image_size, batch_size, level, device):
         """Noised low-res conditioning of a cascade stage (:2443-2449 / elucidated_imagen.py:699-705)."""
         times = self.lowres_noise_schedule.get_times(batch_size, level, device=device)
@@ -285,7 +293,7 @@ class Imagen(_SamplerBase):
         """Imagen.p_sample_loop (:2167-2289): T ancestral steps; one CUDA-graph replay per step."""
         inpaint_resample_times = unsupported.pop('inpaint_resample_times', 5)
         inpaint_images = default(unsupported.pop('inpaint_videos', None), inpaint_images)
-        for name, val in dict(cond_images=cond_images, **unsupported).items():
+        for name, val in unsupported.items():
             if exists(val):
                 raise NotImplementedError(f'p_sample_loop({name}=...) is outside the B200 sampling hot path')
         assert not (cond_scale != 1. and not self.can_classifier_guidance), \
@@ -303,7 +311,7 @@ class Imagen(_SamplerBase):
             coefs, log_snr = noise_scheduler.ddpm_coefficients(device)
             keep = torch.cat((torch.ones(B, dtype=torch.bool, device=device), torch.zeros(R - B, dtype=torch.bool, device=device)))
             plan.prepare(log_snr, text_embeds=text_embeds, text_mask=text_mask, keep=keep, lowres_cond_img=lowres_cond_img,
-                         lowres_noise_times=self.lowres_noise_schedule.get_condition(lowres_noise_times))
+                         lowres_noise_times=self.lowres_noise_schedule.get_condition(lowres_noise_times), cond_images=cond_images)
             chw = Cimg * H * W
             q_lo, q_hi, q_w = quantile_ranks(chw, self.dynamic_thresholding_percentile, device)
             x = plan.x_in
@@ -413,12 +421,12 @@ class Imagen(_SamplerBase):
         was_training = self.training
         self.eval()
         try:
-            return self._sample(texts, text_masks, text_embeds, dict(video_frames=video_frames, cond_images=cond_images,
+            return self._sample(texts, text_masks, text_embeds, dict(video_frames=video_frames,
                                 cond_video_frames=cond_video_frames, post_cond_video_frames=post_cond_video_frames, inpaint_videos=inpaint_videos),
                                 batch_size, cond_scale, lowres_sample_noise_level, start_at_unet_number, start_image_or_video,
                                 stop_at_unet_number, return_all_unet_outputs, return_pil_images, device, use_tqdm,
                                 options=dict(inpaint_images=inpaint_images, inpaint_masks=inpaint_masks, inpaint_resample_times=inpaint_resample_times,
-                                             init_images=init_images, skip_steps=skip_steps))
+                                             init_images=init_images, skip_steps=skip_steps, cond_images=cond_images))
         finally:
             self.train(was_training)
 
@@ -427,6 +435,10 @@ class Imagen(_SamplerBase):
         options = dict(options or {})
         device = default(device, self.device)
         self.reset_unets_all_one_device(device=device)
+        cond_images = options.get('cond_images')
+        if exists(cond_images) and cond_images.dtype == torch.uint8:          # cast_uint8_images_to_float (:91-94, :2324)
+            cond_images = cond_images / 255
+        self._check_cond_images(cond_images, start_at_unet_number, stop_at_unet_number)
         self._check_sample_args(texts, text_embeds, text_masks, unsupported)
         if return_pil_images:
             raise NotImplementedError('return_pil_images: convert the returned tensor yourself')
@@ -471,7 +483,7 @@ class Imagen(_SamplerBase):
                                      pred_objective=pred_objective, dynamic_threshold=dynamic_threshold, use_tqdm=use_tqdm,
                                      inpaint_images=inpaint_images, inpaint_masks=inpaint_masks,
                                      inpaint_resample_times=options.get('inpaint_resample_times', 5), init_images=unet_init_images,
-                                     skip_steps=unet_skip_steps)
+                                     skip_steps=unet_skip_steps, cond_images=cond_images)
             launches += self.last_launch_count
             outputs.append(img)
             if exists(stop_at_unet_number) and stop_at_unet_number == unet_number:

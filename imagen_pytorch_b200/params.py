@@ -45,9 +45,9 @@ UNET_DEFAULTS = OrderedDict(
 # They raise instead of silently diverging (SURVEY.md section 7 "API edge cases").
 _UNSUPPORTED = dict(
     use_linear_attn=lambda v: any(cast_tuple(v)), use_linear_cross_attn=lambda v: any(cast_tuple(v)),
-    cross_embed_downsample=bool, cond_images_channels=lambda v: v > 0,
+    cross_embed_downsample=bool,
     combine_upsample_fmaps=bool, init_conv_to_final_conv_residual=bool,
-    pixel_shuffle_upsample=lambda v: not v, attn_dim_head=lambda v: v != 64,
+    pixel_shuffle_upsample=lambda v: not v, attn_dim_head=lambda v: v > 64 or v < 1,
     final_resnet_block=lambda v: not v,
 )
 
@@ -77,7 +77,8 @@ class UnetArch:
         self.lowres_cond = bool(g('lowres_cond'))
         self.cond_on_text = bool(g('cond_on_text'))
         self.self_cond = bool(g('self_cond'))
-        self.init_channels = self.channels * (1 + int(self.lowres_cond) + int(self.self_cond))      # :1184
+        self.cond_images_channels = int(g('cond_images_channels'))
+        self.init_channels = self.channels * (1 + int(self.lowres_cond) + int(self.self_cond)) + self.cond_images_channels   # :1184, :1194
         self.init_dim = g('init_dim') if g('init_dim') is not None else self.dim
         self.dims = [self.init_dim, *[self.dim * m for m in g('dim_mults')]]
         self.in_out = list(zip(self.dims[:-1], self.dims[1:]))
@@ -329,3 +330,40 @@ def build_param_tree(root: nn.Module, table):
                 node.add_module(name, child)
             node = child
         node.register_parameter(parts[-1], nn.Parameter(_init_tensor(shape, kind)))
+
+
+# ----------------------------------------------------------------------------------------------
+# attention head width.  The sm_100a attention kernels work on 64-wide heads (one 128-byte swizzle row per key).  Narrower heads
+# (the reference's UnetConfig defaults to attn_dim_head=32, configs.py:49-50) run on the same kernels with every head zero-padded
+# to 64 channels: q.k, the L2 norms and P.V are unchanged by zero channels, and the padded output channels meet zero columns of
+# to_out.  Only the packed operands are padded -- the module's state_dict keeps the reference layout.
+# ----------------------------------------------------------------------------------------------
+HEAD_PAD = 64
+_PAD_DIM0 = ('.to_q.weight', '.to_kv.weight', '.to_context.1.weight', '.to_context.1.bias', '.q_scale', '.k_scale')
+
+
+def pad_attention_heads(sd, dim_head):
+    """{key: tensor} of every attention parameter of `sd` (host tensors) re-laid out for 64-wide heads; {} when dim_head == 64."""
+    if dim_head == HEAD_PAD:
+        return {}
+    assert dim_head < HEAD_PAD
+    out = {}
+    for k, v in sd.items():
+        if k.startswith(('mid_block1.', 'mid_block2.')):      # plain ResnetBlock(mid_dim): CrossAttention defaults heads=8, dim_head=64 (:1380, :1382)
+            continue
+        if k.endswith(_PAD_DIM0) and ('attn' in k or '.layers.' in k):
+            assert v.shape[0] % dim_head == 0, (k, tuple(v.shape))
+            g = v.reshape(v.shape[0] // dim_head, dim_head, *v.shape[1:])
+            p = g.new_zeros(g.shape[0], HEAD_PAD, *g.shape[2:])
+            p[:, :dim_head] = g
+            out[k] = p.reshape(g.shape[0] * HEAD_PAD, *g.shape[2:]).contiguous()
+        elif k.endswith('.null_kv'):
+            p = v.new_zeros(*v.shape[:-1], HEAD_PAD)
+            p[..., :dim_head] = v
+            out[k] = p.contiguous()
+        elif k.endswith('.to_out.0.weight') and v.ndim == 2 and v.shape[1] % dim_head == 0 and ('attn' in k or '.layers.' in k):
+            g = v.reshape(v.shape[0], v.shape[1] // dim_head, dim_head)
+            p = g.new_zeros(g.shape[0], g.shape[1], HEAD_PAD)
+            p[..., :dim_head] = g
+            out[k] = p.reshape(g.shape[0], -1).contiguous()
+    return out

@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _lib, ops
 from ._lib import Src, TimeRowJob
-from .params import UnetArch, param_table, build_param_tree
+from .params import UnetArch, param_table, build_param_tree, pad_attention_heads
 
 LOG2E = 1.4426950408889634
 BF16 = torch.bfloat16
@@ -127,6 +127,12 @@ class UnetPlan:
         self._keep, self._post = [], []
         self._act = _Arena(device, zero=True, chunk=1 << 30)      # activations / state: zero-filled chunks (one fill kernel per GiB)
         self._wts = _Arena(device, zero=False, chunk=1 << 28, staged=True)
+        # heads narrower than 64 channels run zero-padded to 64 on the same kernels (params.pad_attention_heads); from here on both
+        # parameter views describe 64-wide heads
+        for k, v in pad_attention_heads(self.sdc, a.dim_head).items():
+            self.sdc[k] = v
+            self.sd[k] = self._wts.put(v)
+        self.inner = a.heads * 64
         self._ops = []
         self._jobs = []
         self.cross_layers, self.self_layers = [], []
@@ -140,6 +146,8 @@ class UnetPlan:
         # self-conditioning input (imagen_pytorch.py:1541-1543): the samplers' step kernels write x_start here, zeros before the first step
         self.sc_in = self._zeros((B, a.channels, H, W), torch.float32) if a.self_cond else None
         self.lowres_img = self._zeros((B, a.channels, H, W), torch.float32) if a.lowres_cond else None
+        # conditioning image (Unet(cond_images_channels > 0), :1553-1560): static over the t-loop, resized once in prepare()
+        self.cond_img = self._zeros((B, a.cond_images_channels, H, W), torch.float32) if a.cond_images_channels else None
         self.pred = self._zeros((R, a.channels_out, H, W), torch.float32)
         self.slots = self._zeros((R,), torch.int32)
         self.time_cond_table = self._zeros((n_slots, a.time_cond_dim), torch.float32)
@@ -392,7 +400,7 @@ class UnetPlan:
         """TransformerBlock.forward (imagen_pytorch.py:1012-1022): multi-query self-attention + feed-forward."""
         a, sd, R = self.arch, self.sdc, self.R
         n, M, Cc = x.H * x.W, x.rows, x.C
-        heads, inner = a.heads, a.inner
+        heads, inner = a.heads, self.inner
         for l in range(depth):
             q_, ff = f'{p}.layers.{l}.0', f'{p}.layers.{l}.1'
             xn = self._prenorm_ln(x, sd[q_ + '.norm.g'])
@@ -484,9 +492,11 @@ class UnetPlan:
         patches = self._new(M0, Kinit)
         stem = []
         self._ops = stem
-        imgs = [self.x_in] + ([self.sc_in] if a.self_cond else []) + ([self.lowres_img] if a.lowres_cond else [])   # cat order :1543, :1551
-        imgs += [None] * (3 - len(imgs))
-        self._add('b200_im2col_init3', *[v for im in imgs for v in ((im.data_ptr(), a.channels) if im is not None else (None, 0))],
+        # cat order: (cond_images, x, self_cond, lowres_cond_img) (:1543, :1551, :1560)
+        imgs = ([self.cond_img] if a.cond_images_channels else []) + [self.x_in] + ([self.sc_in] if a.self_cond else []) + \
+               ([self.lowres_img] if a.lowres_cond else [])
+        imgs += [None] * (4 - len(imgs))
+        self._add('b200_im2col_init4', *[v for im in imgs for v in ((im.data_ptr(), im.shape[1]) if im is not None else (None, 0))],
                   B, H, W, ks, patches.ptr, Kinit)
         Wi = torch.zeros(a.init_dim, ks, ks, Cin)
         bi = torch.zeros(a.init_dim)
@@ -648,7 +658,7 @@ class UnetPlan:
         ml = self._lin(self._ln(pooled, sd[p + '.to_latents_from_mean_pooled_seq.0.g']),
                        sd[p + '.to_latents_from_mean_pooled_seq.1.weight'], sd[p + '.to_latents_from_mean_pooled_seq.1.bias'])
         latents = torch.cat((ml.view(T, a.pool_mean_latents, cd), latents), dim=1).contiguous()
-        nl, inner, H = latents.shape[1], a.inner, a.heads
+        nl, inner, H = latents.shape[1], self.inner, a.heads
         for l in range(a.pool_depth):
             q_, ff = f'{p}.layers.{l}.0', f'{p}.layers.{l}.1'
             xn = self._ln(x_pos, sd[q_ + '.norm.weight'], sd[q_ + '.norm.bias'])
@@ -666,7 +676,7 @@ class UnetPlan:
 
     @torch.no_grad()
     def prepare(self, times, *, text_embeds=None, text_mask=None, keep=None, lowres_cond_img=None, lowres_noise_times=None,
-                slot_of_row=None):
+                slot_of_row=None, cond_images=None):
         """Everything of Unet.forward that does not depend on x (imagen_pytorch.py:1573-1660), for all schedule slots.
 
         times: fp32 [S'] U-Net time input per schedule slot (S' <= n_slots).
@@ -679,6 +689,15 @@ class UnetPlan:
         cd, tcd, ntt = a.cond_dim, a.time_cond_dim, self.ntt
         keep = torch.ones(R, dtype=torch.bool, device=dev) if keep is None else keep.to(dev)
         img_of_row = torch.arange(R, device=dev) % B
+        assert not ((a.cond_images_channels > 0) ^ (cond_images is not None)), \
+            'you either requested to condition on an image on the unet, but the conditioning image is not supplied, or vice versa'
+        if cond_images is not None:                                             # :1557-1560 (the concat itself happens in the stem gather)
+            assert cond_images.shape[1] == a.cond_images_channels, \
+                'the number of channels on the conditioning image you are passing in does not match what you specified on initialiation of the unet'
+            ci = cond_images.to(device=dev, dtype=torch.float32)
+            if ci.shape[-1] != self.W:
+                ci = F.interpolate(ci, self.W, mode=a.cfg['resize_mode'])
+            self.cond_img.copy_(ci)
 
         def time_path(prefix, tvals):                                          # :1573-1578 / :1584-1586
             n = tvals.numel()
@@ -784,7 +803,8 @@ class Unet(nn.Module):
         self.channels, self.channels_out = a.channels, a.channels_out
         self.lowres_cond, self.cond_on_text = a.lowres_cond, a.cond_on_text
         self.self_cond = a.self_cond
-        self.has_cond_image = False
+        self.has_cond_image = a.cond_images_channels > 0
+        self.cond_images_channels = a.cond_images_channels
         self.max_text_len = a.max_text_len
         build_param_tree(self, param_table(a))
         self._plans = {}
@@ -831,12 +851,12 @@ class Unet(nn.Module):
         return self._plans[key]
 
     @torch.no_grad()
-    def _run(self, x, time, keep_rows, R, *, lowres_cond_img, lowres_noise_times, text_embeds, text_mask, self_cond=None):
+    def _run(self, x, time, keep_rows, R, *, lowres_cond_img, lowres_noise_times, text_embeds, text_mask, self_cond=None, cond_images=None):
         B, _, H, W = x.shape
         plan = self.plan(R, B, H, W, B, x.device)
         with torch.cuda.device(x.device):
             plan.prepare(time, text_embeds=text_embeds, text_mask=text_mask, keep=keep_rows, lowres_cond_img=lowres_cond_img,
-                         lowres_noise_times=lowres_noise_times, slot_of_row=torch.arange(R, device=x.device) % B)
+                         lowres_noise_times=lowres_noise_times, slot_of_row=torch.arange(R, device=x.device) % B, cond_images=cond_images)
             plan.x_in.copy_(x.to(torch.float32))
             if self.self_cond:                                                  # default: zeros_like(x) (:1542)
                 plan.sc_in.zero_() if self_cond is None else plan.sc_in.copy_(self_cond.to(torch.float32))
@@ -848,8 +868,6 @@ class Unet(nn.Module):
                 cond_images=None, self_cond=None, cond_drop_prob=0.):
         assert not (self.lowres_cond and lowres_cond_img is None), 'low resolution conditioning image must be present'
         assert not (self.lowres_cond and lowres_noise_times is None), 'low resolution conditioning noise time must be present'
-        if cond_images is not None:
-            raise NotImplementedError('cond_images is outside the B200 hot path')
         B = x.shape[0]
         if cond_drop_prob == 1:
             keep = torch.zeros(B, dtype=torch.bool, device=x.device)
@@ -858,19 +876,18 @@ class Unet(nn.Module):
         else:                                                                   # prob_mask_like (:201-207)
             keep = torch.zeros(B, device=x.device).float().uniform_(0, 1) < (1 - cond_drop_prob)
         out = self._run(x, time, keep, B, lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
-                        text_embeds=text_embeds, text_mask=text_mask, self_cond=self_cond)
+                        text_embeds=text_embeds, text_mask=text_mask, self_cond=self_cond, cond_images=cond_images)
         return out.clone()
 
     @torch.no_grad()
     def forward_with_cond_scale(self, x, time, *, cond_scale=1., **kwargs):    # :1510-1522
         if cond_scale == 1:
             return self.forward(x, time, **kwargs)
-        if kwargs.get('cond_images') is not None:
-            raise NotImplementedError('cond_images is outside the B200 hot path')
         B = x.shape[0]
         keep = torch.cat((torch.ones(B, dtype=torch.bool, device=x.device), torch.zeros(B, dtype=torch.bool, device=x.device)))
         out = self._run(x, time, keep, 2 * B, lowres_cond_img=kwargs.get('lowres_cond_img'), lowres_noise_times=kwargs.get('lowres_noise_times'),
-                        text_embeds=kwargs.get('text_embeds'), text_mask=kwargs.get('text_mask'), self_cond=kwargs.get('self_cond'))
+                        text_embeds=kwargs.get('text_embeds'), text_mask=kwargs.get('text_mask'), self_cond=kwargs.get('self_cond'),
+                        cond_images=kwargs.get('cond_images'))
         logits, null_logits = out[:B], out[B:]
         return null_logits + (logits - null_logits) * cond_scale
 

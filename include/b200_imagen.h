@@ -197,6 +197,10 @@ int b200_im2col_init(const float* img0, int C0, const float* img1, int C1, int B
 /* the same with a third NCHW source (channel order img0 | img1 | img2): x | self_cond | lowres_cond_img (imagen_pytorch.py:1541-1551) */
 int b200_im2col_init3(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2, int B, int H, int W,
                       int ksize, void* out, int32_t Kpad, void* stream);
+/* the same with a fourth image (Unet(cond_images_channels > 0): cat((cond_images, x [, self_cond] [, lowres_cond_img])),
+ * imagen_pytorch.py:1553-1560) */
+int b200_im2col_init4(const float* img0, int C0, const float* img1, int C1, const float* img2, int C2,
+                      const float* img3, int C3, int B, int H, int W, int ksize, void* out, int32_t Kpad, void* stream);
 
 /* Pixel-unshuffle gather of Downsample (imagen_pytorch.py:638): out[b,h,w,(s1,s2,c)] = x[b,2h+s1,2w+s2,c]. */
 int b200_pixel_unshuffle(const void* x, int32_t ldx, int B, int H, int W, int C, void* out, void* stream);

@@ -378,6 +378,34 @@ def main():
     big['cfg0_50steps'] = dict(kwargs=kw0, wseed=15, iseed=106, seed=83, timesteps=50, out=r50)
     torch.save(big, os.path.join(out_dir, 'baseline_shapes.pt'))
 
+    # ---------------------------------------------------------------- 5g. boundary options: attn_dim_head = 32 (the reference's UnetConfig default,
+    # configs.py:49-50) with attn_heads = 4, and cond_images (imagen_pytorch.py:1553-1560) -- forward + a 3-step CFG DDPM sample
+    dh_kw = dict(dim=32, dim_mults=(1, 2, 4), text_embed_dim=64, max_text_len=24, attn_dim_head=32, attn_heads=4, cond_images_channels=3)
+    udh, sddh, cfgdh = build('dh32_cond', dh_kw, 17)
+    gdh = torch.Generator().manual_seed(107)
+    xdh = torch.randn(B, 3, 32, 32, generator=gdh)
+    cimg = torch.rand(B, 3, 16, 16, generator=gdh)                  # half resolution: resized (nearest) inside the U-Net
+    with torch.no_grad():
+        r_dh = udh(xdh, t, text_embeds=te, text_mask=tm, cond_images=cimg)
+        r_dh0 = udh(xdh, t, text_embeds=te, text_mask=tm, cond_images=cimg, cond_drop_prob=1.)
+        o_dh = unet_ref.unet_forward(sddh, cfgdh, xdh, t, text_embeds=te, text_mask=tm, cond_images=cimg)
+        o_dh0 = unet_ref.unet_forward(sddh, cfgdh, xdh, t, text_embeds=te, text_mask=tm, cond_images=cimg, cond_drop_prob=1.)
+    for name, a, b in (('cond', r_dh, o_dh), ('null', r_dh0, o_dh0)):
+        d = _maxdiff(a, b)
+        print(f'[unet dim_head 32 + cond_images {name}] ref-vs-oracle max|d| = {d:.3e}')
+        assert d < 1e-5 * max(1., a.abs().max().item())
+    im_dh = ref.Imagen(unets=ref.Unet(**dh_kw), image_sizes=32, timesteps=3, text_embed_dim=64)
+    im_dh.unets[0].load_state_dict(sddh)
+    torch.manual_seed(89)
+    r_dhs = im_dh.sample(text_embeds=te, cond_images=cimg, cond_scale=2., use_tqdm=False)
+    torch.manual_seed(89)
+    o_dhs = sampler_ref.imagen_sample([(sddh, cfgdh)], (32,), text_embeds=te, timesteps=3, cond_scale=2., cond_images=cimg)
+    d = _maxdiff(r_dhs, o_dhs)
+    print(f'[ddpm dim_head 32 + cond_images sample] ref-vs-oracle max|d| = {d:.3e}')
+    assert d < 1e-4
+    torch.save(dict(kwargs=dh_kw, wseed=17, x=xdh, t=t, text_embeds=te, text_mask=tm, cond_images=cimg, out_cond=r_dh, out_null=r_dh0,
+                    timesteps=3, cond_scale=2., seed=89, out_sample=r_dhs), os.path.join(out_dir, 'unet_dh32_cond_dim32.pt'))
+
     # ---------------------------------------------------------------- 6. schedule / scalar known answers
     tt = torch.tensor([1., .75, .5, .25, 0., 0.2])
     torch.save(dict(t=tt, cosine=ref.imagen_pytorch.alpha_cosine_log_snr(tt), linear=ref.imagen_pytorch.beta_linear_log_snr(tt),
@@ -385,7 +413,7 @@ def main():
 
     # ---------------------------------------------------------------- 7. state_dict key/shape contract of the default configs
     contract = {'test_base': shapes_out['base'], 'test_sr': shapes_out['sr'], 'test_selfcond': shapes_out['selfcond'],
-                'base_dim192': shapes_out['base_dim192'], 'srunet1024_t64': shapes_out['srunet1024_t64']}
+                'base_dim192': shapes_out['base_dim192'], 'srunet1024_t64': shapes_out['srunet1024_t64'], 'test_dh32_cond': shapes_out['dh32_cond']}
     for name, kw in (('base_dim128', dict(dim=128)), ('base_dim32', dict(dim=32, dim_mults=(1, 2, 4, 8)))):
         torch.manual_seed(0)
         m = ref.Unet(**kw)

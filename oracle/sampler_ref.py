@@ -154,7 +154,7 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
                   noise_schedules=('cosine',), lowres_sample_noise_level=0.2, dynamic_thresholding=True,
                   pred_objectives='noise', stop_at_unet_number=None, return_all_unet_outputs=False, trace=None,
                   randn=torch.randn, init_images=None, skip_steps=None, inpaint_images=None, inpaint_masks=None,
-                  inpaint_resample_times=5, start_at_unet_number=1, start_image=None):
+                  inpaint_resample_times=5, start_at_unet_number=1, start_image=None, cond_images=None):
     """Imagen.sample (imagen_pytorch.py:2291-2498), text_embeds path, no video.
     unets: list of (state_dict, cfg).  start_at_unet_number / start_image: the upscale-only entry (:2396-2403)."""
     n = len(unets)
@@ -178,6 +178,8 @@ def imagen_sample(unets, image_sizes, *, text_embeds, text_masks=None, timesteps
         if i + 1 < start_at_unet_number:                                       # :2412-2414
             continue
         kw = dict(text_embeds=text_embeds, text_mask=text_masks)
+        if cond_images is not None:
+            kw['cond_images'] = cond_images                                    # :2465 (the U-Net resizes it, :1559)
         lowres_log_snr = None
         opt = dict(skip_steps=skip_steps[i], inpaint_resample_times=inpaint_resample_times)
         if init_images[i] is not None:

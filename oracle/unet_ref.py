@@ -247,10 +247,9 @@ def _upsample(x, sd, p, pixel_shuffle):               # PixelShuffleUpsample :60
 
 
 def unet_forward(sd, cfg, x, time, *, text_embeds=None, text_mask=None,
-                 lowres_cond_img=None, lowres_noise_times=None, cond_drop_prob=0., self_cond=None):
-    """Unet.forward, imagen_pytorch.py:1524-1725 (cond_images / combine_upsample_fmaps /
-    init_conv_to_final_conv_residual branches omitted: out of scope per SURVEY.md section 8a;
-    the product rejects them too)."""
+                 lowres_cond_img=None, lowres_noise_times=None, cond_drop_prob=0., self_cond=None, cond_images=None):
+    """Unet.forward, imagen_pytorch.py:1524-1725 (combine_upsample_fmaps / init_conv_to_final_conv_residual
+    branches omitted: out of scope per SURVEY.md section 8a; the product rejects them too)."""
     heads = cfg['attn_heads']
     batch = x.shape[0]
     nlev = len(cfg['dim_mults'])
@@ -263,6 +262,12 @@ def unet_forward(sd, cfg, x, time, *, text_embeds=None, text_mask=None,
     assert not (cfg['lowres_cond'] and lowres_cond_img is None)
     if lowres_cond_img is not None:
         x = torch.cat((x, lowres_cond_img), dim=1)                             # :1550-1551
+    assert not ((cfg.get('cond_images_channels', 0) > 0) ^ (cond_images is not None))           # :1555
+    if cond_images is not None:                                                # :1557-1560
+        assert cond_images.shape[1] == cfg['cond_images_channels']
+        if cond_images.shape[-1] != x.shape[-1]:
+            cond_images = F.interpolate(cond_images, x.shape[-1], mode=cfg.get('resize_mode', 'nearest'))   # resize_image_to :152-168
+        x = torch.cat((cond_images, x), dim=1)
 
     if cfg['init_cross_embed']:                                                # CrossEmbedLayer :1074-1076
         ks = sorted(cfg['init_cross_embed_kernel_sizes'])

@@ -166,6 +166,36 @@ def test_srunet1024_architecture_upscale_only_matches_oracle():
     assert out.shape == (2, 3, 128, 128) and s['mean_abs'] < 1e-2 and s['max_abs'] < 0.15
 
 
+# ------------------------------------------------------------------------------------------------ boundary options
+
+def test_dim_head_32_and_cond_images_forward_and_sample():
+    """Unet(attn_dim_head=32, attn_heads=4, cond_images_channels=3): heads zero-padded to the kernels' 64-wide head layout
+    (params.pad_attention_heads), conditioning image as a fourth stem source (b200_im2col_init4) -- forward against the live
+    reference's golden, 3-step CFG DDPM sample against the oracle on the same noise."""
+    from tests.helpers import synth_weights
+    g = load_golden('unet_dh32_cond_dim32.pt')
+    sd = synth_weights('test_dh32_cond', g['wseed'])
+    u = b2.Unet(**g['kwargs'])
+    u.load_state_dict(sd)
+    u = u.to(DEV)
+    kw = dict(text_embeds=g['text_embeds'].to(DEV), text_mask=g['text_mask'].to(DEV), cond_images=g['cond_images'].to(DEV))
+    out = u(g['x'].to(DEV), g['t'].to(DEV), **kw)
+    out0 = u(g['x'].to(DEV), g['t'].to(DEV), cond_drop_prob=1., **kw)
+    e, e0 = rel_err(out, g['out_cond']), rel_err(out0, g['out_null'])
+    im = b2.Imagen(u, image_sizes=32, timesteps=g['timesteps'], text_embed_dim=64).to(DEV)
+    torch.manual_seed(3)
+    img = im.sample(text_embeds=g['text_embeds'].to(DEV), cond_images=g['cond_images'].to(DEV), cond_scale=g['cond_scale'], use_tqdm=False)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        ref = sampler_ref.imagen_sample([(sd, unet_ref.unet_config(**g['kwargs']))], (32,), text_embeds=g['text_embeds'], timesteps=g['timesteps'],
+                                        cond_scale=g['cond_scale'], cond_images=g['cond_images'], randn=cuda_randn)
+    s = image_stats(img, ref)
+    record('dim_head32_cond_images', fwd_cond=e, fwd_null=e0, **s)
+    assert e < 3e-2 and e0 < 3e-2 and s['mean_abs'] < 1e-2
+    with pytest.raises(AssertionError):                     # cond image required once the U-Net was built with cond_images_channels (:1555)
+        im.sample(text_embeds=g['text_embeds'].to(DEV), cond_scale=1., use_tqdm=False)
+
+
 # ------------------------------------------------------------------------------------------------ plan cache (ADVICE r01)
 
 def test_plan_and_step_graph_are_reused_across_sample_calls_and_track_weight_updates():

@@ -97,8 +97,10 @@ def test_sample_argument_validation_mirrors_reference():
         im.sample(use_tqdm=False)                                               # text required
     with pytest.raises(NotImplementedError):
         im.sample(texts=['a cat'], use_tqdm=False)                              # T5 encoder out of scope
+    with pytest.raises(AssertionError):                                           # cond_images for a U-Net built without cond_images_channels (:1555)
+        im.sample(text_embeds=torch.randn(1, 8, 64), cond_images=torch.zeros(1, 3, 16, 16), use_tqdm=False)
     with pytest.raises(NotImplementedError):
-        im.sample(text_embeds=torch.randn(1, 8, 64), cond_images=torch.zeros(1, 3, 16, 16), use_tqdm=False)                      # out of the hot path
+        im.sample(text_embeds=torch.randn(1, 8, 64), video_frames=4, use_tqdm=False)                                              # video: out of the hot path
     with pytest.raises(AssertionError):                                           # inpainting batch must match the text batch (:2343-2350)
         im.sample(text_embeds=torch.randn(1, 8, 64), inpaint_images=torch.zeros(2, 3, 16, 16), inpaint_masks=torch.zeros(2, 16, 16), use_tqdm=False)
 

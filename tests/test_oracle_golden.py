@@ -172,3 +172,20 @@ def test_baseline_shape_fixture_is_complete():
     for name in ('base_dim128', 'base_dim192', 'base_dim32', 'srunet256', 'srunet1024_t64'):
         assert name in c and len(c[name]) > 100
     assert torch.allclose(g['dim128']['out_cfg3'], g['dim128']['out_null'] + (g['dim128']['out_cond'] - g['dim128']['out_null']) * 3.)
+
+
+def test_dim_head_32_and_cond_images_match_reference_golden():
+    """attn_dim_head = 32 / attn_heads = 4 (the reference's UnetConfig default head width) + cond_images (imagen_pytorch.py:1553-1560)."""
+    g = load_golden('unet_dh32_cond_dim32.pt')
+    sd = synth_weights('test_dh32_cond', g['wseed'])
+    cfg = unet_ref.unet_config(**g['kwargs'])
+    kw = dict(text_embeds=g['text_embeds'], text_mask=g['text_mask'], cond_images=g['cond_images'])
+    with torch.no_grad():
+        out = unet_ref.unet_forward(sd, cfg, g['x'], g['t'], **kw)
+        out0 = unet_ref.unet_forward(sd, cfg, g['x'], g['t'], cond_drop_prob=1., **kw)
+    assert (out - g['out_cond']).abs().max() < 1e-4 and (out0 - g['out_null']).abs().max() < 1e-4
+    torch.manual_seed(g['seed'])
+    with torch.no_grad():
+        img = sampler_ref.imagen_sample([(sd, cfg)], (32,), text_embeds=g['text_embeds'], timesteps=g['timesteps'], cond_scale=g['cond_scale'],
+                                        cond_images=g['cond_images'])
+    assert (img - g['out_sample']).abs().max() < 1e-4

@@ -10,6 +10,7 @@ CASES = {
     'base_dim128': dict(dim=128),
     'base_dim32': dict(dim=32, dim_mults=(1, 2, 4, 8)),
     'base_dim192': dict(dim=192),
+    'test_dh32_cond': dict(dim=32, dim_mults=(1, 2, 4), text_embed_dim=64, max_text_len=24, attn_dim_head=32, attn_heads=4, cond_images_channels=3),
     'srunet1024_t64': dict(dim=128, dim_mults=(1, 2, 4, 8), num_resnet_blocks=(2, 4, 8, 8), layer_attns=False, layer_cross_attns=(False, False, False, True),
                            attn_heads=8, ff_mult=2., memory_efficient=True, lowres_cond=True, text_embed_dim=64),
     'test_base': dict(dim=32, dim_mults=(1, 2, 4, 8), text_embed_dim=64, max_text_len=24),
@@ -45,7 +46,7 @@ def test_fresh_unet_final_conv_is_zero_like_reference():
     assert u.final_conv.weight.abs().max() == 0 and u.final_conv.bias.abs().max() == 0   # zero_init_ :1438
 
 
-@pytest.mark.parametrize('kw', [dict(use_linear_attn=True), dict(init_conv_to_final_conv_residual=True), dict(cond_images_channels=3), dict(attn_dim_head=32),
+@pytest.mark.parametrize('kw', [dict(use_linear_attn=True), dict(init_conv_to_final_conv_residual=True), dict(attn_dim_head=128),
                                 dict(pixel_shuffle_upsample=False), dict(combine_upsample_fmaps=True), dict(cross_embed_downsample=True)])
 def test_unsupported_options_raise_instead_of_diverging(kw):
     with pytest.raises(NotImplementedError):
