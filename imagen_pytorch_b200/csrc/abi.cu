@@ -1,6 +1,7 @@
 // Error plumbing + device checks of the C-ABI (include/b200_imagen.h).
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -9,6 +10,14 @@ void b200_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool b200_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_IMAGEN_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 
 extern "C" const char* b200_last_error(void) { return g_err; }

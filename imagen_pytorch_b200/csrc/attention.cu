@@ -69,6 +69,8 @@ __device__ __forceinline__ void load_kv_tile(uint8_t* sK, uint8_t* sV, const __n
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attn_kernel(AttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t att_smem[];
   uint8_t* sQ = att_smem;                       // 128 x 128 B
   uint8_t* sK = sQ + ATT_BM * 128;              // 2 x 64 x 128 B
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) flash_attn_kernel(AttnParams p
 constexpr int XA_QBUF = 3;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) cross_attn_fewkeys_kernel(AttnParams p, int tiles_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t att_smem[];
   uint8_t* sK = att_smem;                        // 64 x 128 B
   uint8_t* sV = sK + ATT_BN * 128;               // 64 x 128 B
@@ -407,15 +411,13 @@ extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs
       if (splits > ntiles) splits = ntiles;
       const int tiles_per_cta = (ntiles + splits - 1) / splits;
       dim3 xgrid((ntiles + tiles_per_cta - 1) / tiles_per_cta, n_heads, B);
-      cross_attn_fewkeys_kernel<<<xgrid, ATT_THREADS, xsmem, st>>>(p, tiles_per_cta);
-      B200_LAUNCH_OK();
+      B200_CUDA_OK(b200_launch(cross_attn_fewkeys_kernel, xgrid, dim3(ATT_THREADS), xsmem, st, p, tiles_per_cta));
       return B200_OK;
     }
   }
   constexpr int smem = ATT_BM * 128 + 4 * ATT_BN * 128;
   B200_SMEM_OPT_IN(flash_attn_kernel, smem);
   dim3 grid((rows + ATT_BM - 1) / ATT_BM, n_heads, B);
-  flash_attn_kernel<<<grid, ATT_THREADS, smem, st>>>(p);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(flash_attn_kernel, grid, dim3(ATT_THREADS), smem, st, p));
   return B200_OK;
 }

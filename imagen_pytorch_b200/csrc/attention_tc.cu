@@ -320,6 +320,7 @@ template <int POLY, int SUB>   // POLY: every POLY-th exponential goes to the FM
 __global__ void __launch_bounds__(128 + 256 * SUB, 1)
 flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // [2] query tiles
@@ -360,6 +361,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -548,6 +550,7 @@ template <int POLY, int SUB, bool ORDER>   // POLY: every POLY-th exponential on
 __global__ void __launch_bounds__(128 + 256 * SUB, 1)
 flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;                                   // [2] query tiles
@@ -593,6 +596,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -850,7 +854,7 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_pp_kernel<POLY, SUB>), PP_SMEM);                                                                  \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
-    flash_attn_pp_kernel<POLY, SUB><<<grid2, 128 + 256 * SUB, PP_SMEM, st>>>(mq, mk, mv, p);                                      \
+    B200_CUDA_OK(b200_launch(flash_attn_pp_kernel<POLY, SUB>, grid2, dim3(128 + 256 * SUB), PP_SMEM, st, mq, mk, mv, p));           \
   }
     case 10: PP_LAUNCH(4, 1); break;   // ping-pong, 1/4 of the exponentials on the FMA pipe
     case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
@@ -860,7 +864,7 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB, ORDER>), PT_SMEM);                                                           \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
-    flash_attn_pt_kernel<POLY, SUB, ORDER><<<grid2, 128 + 256 * SUB, PT_SMEM, st>>>(mq, mk, mv, p);                               \
+    B200_CUDA_OK(b200_launch(flash_attn_pt_kernel<POLY, SUB, ORDER>, grid2, dim3(128 + 256 * SUB), PT_SMEM, st, mq, mk, mv, p));    \
   }
     case 20: PT_LAUNCH(0, 2, false); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
     case 21: PT_LAUNCH(8, 2, false); break;   // ... + 1/8 of the exponentials on the FMA pipe

@@ -49,6 +49,31 @@ static inline int b200_sm_count() {
   return n[dev];
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A denoising step is ~250 dependent kernels of ~30 us each: with plain stream order every kernel pays its launch latency, block
+// scheduling ramp and prologue (barrier init, TMEM allocation, descriptor prefetch) after the previous grid has drained.  Every
+// per-step kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and executes
+//   pdl_trigger();   at its very top   (lets the NEXT grid be scheduled as soon as all CTAs of this one are running)
+//   ... local set-up that touches no global memory ...
+//   pdl_wait();      before its first global read / write   (returns when the previous grid has completed and flushed)
+// so set-up and launch overlap the predecessor's tail.  The edges are captured into the step CUDA graph as programmatic
+// dependencies.  B200_IMAGEN_PDL=0 launches without the attribute (griddepcontrol.wait is then a no-op).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool b200_pdl_enabled();   // abi.cu
+
+template <class... KArgs, class... Args>
+static inline cudaError_t b200_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- small device helpers

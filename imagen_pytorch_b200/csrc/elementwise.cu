@@ -60,6 +60,8 @@ struct RmsParams {
 
 template <int TPR, int VPT>
 __global__ void __launch_bounds__(ROW_THREADS) rmsnorm_film_silu_kernel(RmsParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int rows_per_block = ROW_THREADS / TPR;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -127,6 +129,8 @@ struct LnParams {
 
 template <int TPR, int VPT>
 __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int rows_per_block = ROW_THREADS / TPR;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
 template <int TPR, int VPT>
 __global__ void __launch_bounds__(ROW_THREADS) gca_logits_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, const float* __restrict__ wk,
                                                                  float bk, float* __restrict__ logits, long long M) {
+  pdl_trigger();
+  pdl_wait();
   const int rows_per_block = ROW_THREADS / TPR;
   const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
   const int t = threadIdx.x % TPR;
@@ -218,6 +224,8 @@ constexpr int GCA_MAX_CHUNK = 1024;   // pixels per chunk held in shared memory
 // softmax-weighted channel sums of one pixel chunk of one sample -> (max, sum, acc[C]) partial
 __global__ void __launch_bounds__(GCA_THREADS) gca_pool_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows_per_sample, int C,
                                                                const float* __restrict__ logits, int nchunk, float* __restrict__ scratch) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sw[GCA_MAX_CHUNK];
   __shared__ float red[GCA_THREADS * 8];
   __shared__ float sred[16];
@@ -282,6 +290,8 @@ __global__ void __launch_bounds__(GCA_THREADS) gca_pool_kernel(const __nv_bfloat
 
 // combine the per-chunk online-softmax partials -> pooled[b, c]
 __global__ void __launch_bounds__(256) gca_combine_kernel(const float* __restrict__ scratch, int nchunk, int C, float* __restrict__ pooled) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const float* sc = scratch + (long long)b * nchunk * (C + 2);
@@ -303,6 +313,8 @@ __global__ void __launch_bounds__(256) gca_combine_kernel(const float* __restric
 template <int MAXB>
 __global__ void __launch_bounds__(256) gca_mlp_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                                                       float* __restrict__ y, int B, int N, int K, int act) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
@@ -337,6 +349,8 @@ __global__ void __launch_bounds__(256) gca_mlp_kernel(const float* __restrict__ 
 __global__ void gate_residual_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ gate,
                                      const __nv_bfloat16* __restrict__ res, int ldr, __nv_bfloat16* __restrict__ out, int ldo,
                                      long long M, int C, int rows_per_sample) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * vecs) return;
@@ -360,6 +374,8 @@ constexpr int IM2COL_ROWS = 32;
 __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restrict__ img0, int C0, const float* __restrict__ img1, int C1,
                                                           const float* __restrict__ img2, int C2, const float* __restrict__ img3, int C3, int B, int H,
                                                           int W, int ks, __nv_bfloat16* __restrict__ out, int Kpad) {
+  pdl_trigger();
+  pdl_wait();
   // k -> (dy, dx, channel) decode table, built once per block instead of a div/mod chain per element
   extern __shared__ int lut[];
   const int Cin = C0 + C1 + C2 + C3, pad = ks / 2, K = ks * ks * Cin;
@@ -406,6 +422,8 @@ __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restric
 
 __global__ void pixel_unshuffle_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W, int C,
                                        __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int H2 = H / 2, W2 = W / 2, vecs = (4 * C) >> 3;
   const long long M2 = (long long)B * H2 * W2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,6 +451,8 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ img, int B, int C,
 
 __global__ void make_time_cond_kernel(const float* __restrict__ table, const float* __restrict__ th, const int* __restrict__ slots, int R,
                                       int D, __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)R * D) return;
   const int r = (int)(idx / D), d = (int)(idx % D);
@@ -441,6 +461,8 @@ __global__ void make_time_cond_kernel(const float* __restrict__ table, const flo
 }
 
 __global__ void update_time_rows_kernel(const b200_timerow_job* __restrict__ jobs, const int* __restrict__ slots) {
+  pdl_trigger();
+  pdl_wait();
   const b200_timerow_job j = jobs[blockIdx.x];
   const int b = blockIdx.y;
   const int n = j.rows * j.width;
@@ -452,7 +474,7 @@ __global__ void update_time_rows_kernel(const b200_timerow_job* __restrict__ job
 }  // namespace
 
 #define LAUNCH_ROW(T, V, KERNEL, grid_rows, ...) \
-  KERNEL<T, V><<<(unsigned)ceil_div64(grid_rows, ROW_THREADS / T), ROW_THREADS, 0, st>>>(__VA_ARGS__)
+  B200_CUDA_OK(b200_launch(KERNEL<T, V>, dim3((unsigned)ceil_div64(grid_rows, ROW_THREADS / T)), dim3(ROW_THREADS), 0, st, __VA_ARGS__))
 #define DISPATCH_VPT(T, vpt, KERNEL, grid_rows, ...)                               \
   switch (vpt) {                                                                   \
     case 1: LAUNCH_ROW(T, 1, KERNEL, grid_rows, __VA_ARGS__); break;               \
@@ -543,14 +565,11 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
   const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
   DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
   B200_LAUNCH_OK();
-  gca_pool_kernel<<<dim3(nchunk, B), GCA_THREADS, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials);
-  B200_LAUNCH_OK();
-  gca_combine_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(partials, nchunk, C, pooled);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(gca_pool_kernel, dim3(nchunk, B), dim3(GCA_THREADS), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials));
+  B200_CUDA_OK(b200_launch(gca_combine_kernel, dim3((C + 255) / 256, B), dim3(256), 0, st, partials, nchunk, C, pooled));
   const int bg = (B + 7) / 8;
-  gca_mlp_kernel<8><<<dim3((hidden * 32 + 255) / 256, bg), 256, 0, st>>>(pooled, w1, b1, hid, B, hidden, C, 1);
-  gca_mlp_kernel<8><<<dim3((C * 32 + 255) / 256, bg), 256, 0, st>>>(hid, w2, b2, gate, B, C, hidden, 2);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(gca_mlp_kernel<8>, dim3((hidden * 32 + 255) / 256, bg), dim3(256), 0, st, pooled, w1, b1, hid, B, hidden, C, 1));
+  B200_CUDA_OK(b200_launch(gca_mlp_kernel<8>, dim3((C * 32 + 255) / 256, bg), dim3(256), 0, st, hid, w2, b2, gate, B, C, hidden, 2));
   return B200_OK;
 }
 
@@ -560,10 +579,9 @@ extern "C" int b200_gate_residual(const void* x, int32_t ldx, const float* gate,
   B200_REQUIRE(x && gate && residual && out && M > 0 && M < (1ll << 31), "gate_residual: null pointer / bad M");
   B200_REQUIRE((C & 7) == 0 && (ldx & 7) == 0 && (ldr & 7) == 0 && (ldo & 7) == 0, "gate_residual: C/strides must be multiples of 8");
   const long long tot = M * (C >> 3);
-  gate_residual_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, gate,
+  B200_CUDA_OK(b200_launch(gate_residual_kernel, dim3((unsigned)ceil_div64(tot, 256)), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, gate,
                                                                         reinterpret_cast<const __nv_bfloat16*>(residual), ldr,
-                                                                        reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C, rows_per_sample);
-  B200_LAUNCH_OK();
+                                                                        reinterpret_cast<__nv_bfloat16*>(out), ldo, M, C, rows_per_sample));
   return B200_OK;
 }
 
@@ -573,9 +591,7 @@ extern "C" int b200_im2col_init4(const float* img0, int C0, const float* img1, i
   B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1) && (C2 == 0 || img2) && (C3 == 0 || img3), "im2col: null pointer");
   B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1 + C2 + C3), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
   B200_REQUIRE(Kpad * 4 <= 48 * 1024 && C0 + C1 + C2 + C3 < 256, "im2col: patch too large");
-  im2col_init_kernel<<<(unsigned)ceil_div64((long long)B * H * W, IM2COL_ROWS), 256, Kpad * sizeof(int), st>>>(
-      img0, C0, img1, C1, img2, C2, img3, C3, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(im2col_init_kernel, dim3((unsigned)ceil_div64((long long)B * H * W, IM2COL_ROWS)), dim3(256), Kpad * sizeof(int), st, img0, C0, img1, C1, img2, C2, img3, C3, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad));
   return B200_OK;
 }
 
@@ -593,9 +609,8 @@ extern "C" int b200_pixel_unshuffle(const void* x, int32_t ldx, int B, int H, in
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(x && out && (C & 7) == 0 && (ldx & 7) == 0 && (H & 1) == 0 && (W & 1) == 0, "pixel_unshuffle: bad args (C=%d H=%d W=%d)", C, H, W);
   const long long tot = (long long)B * (H / 2) * (W / 2) * ((4 * C) >> 3);
-  pixel_unshuffle_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H, W, C,
-                                                                          reinterpret_cast<__nv_bfloat16*>(out));
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(pixel_unshuffle_kernel, dim3((unsigned)ceil_div64(tot, 256)), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, B, H, W, C,
+                                                                          reinterpret_cast<__nv_bfloat16*>(out)));
   return B200_OK;
 }
 
@@ -612,8 +627,7 @@ extern "C" int b200_make_time_cond(const float* table, const float* text_hiddens
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B200_REQUIRE(table && text_hiddens && slots && out && R > 0 && D > 0, "make_time_cond: bad args");
   const long long tot = (long long)R * D;
-  make_time_cond_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(table, text_hiddens, slots, R, D, reinterpret_cast<__nv_bfloat16*>(out));
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(make_time_cond_kernel, dim3((unsigned)ceil_div64(tot, 256)), dim3(256), 0, st, table, text_hiddens, slots, R, D, reinterpret_cast<__nv_bfloat16*>(out)));
   return B200_OK;
 }
 
@@ -622,7 +636,6 @@ extern "C" int b200_update_time_rows(const b200_timerow_job* jobs_dev, int njobs
   if (njobs == 0) return B200_OK;
   B200_REQUIRE(jobs_dev && slots && R > 0 && R <= 65535, "update_time_rows: bad args");
   int threads = max_elems >= 256 ? 256 : (max_elems >= 128 ? 128 : 64);
-  update_time_rows_kernel<<<dim3(njobs, R), threads, 0, st>>>(jobs_dev, slots);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(update_time_rows_kernel, dim3(dim3(njobs, R)), dim3(threads), 0, st, jobs_dev, slots));
   return B200_OK;
 }

@@ -577,9 +577,21 @@ __device__ __forceinline__ void flush32_to(__nv_bfloat16* base, int ld, const Ge
 // back to the MMA warp right after it), every value computed once (a first version re-read TMEM and recomputed bias / GELU /
 // norm1 for each statistics pass: 2-3x the instructions, and with 8 epilogue warps the fused GEMMs became instruction bound --
 // FF1+GELU+LN 102 us vs 45 + 25 us unfused).
-template <int HALVES, class Load32, class Wait32, class Release>
+// sum of n register values with four independent accumulators (a 64-deep dependent FADD chain costs ~256 cycles of latency,
+// and the epilogue warps are latency bound)
+template <int N_, class F>
+__device__ __forceinline__ float sum4(F f) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < N_; j += 4) { a0 += f(j); a1 += f(j + 1); a2 += f(j + 2); a3 += f(j + 3); }
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <int BNH, int HALVES, class Load32, class Wait32, class Release>
 __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo& ri, int n0, uint32_t stage, uint32_t meta, float2* xch, int parity,
                                               int q, int half, int lane, Load32 load32, Wait32 wait32, Release release) {
+  static_assert(BNH == 32 || BNH == 64, "one or two 32-column groups per epilogue warp, kept in registers");
+  constexpr int NG = BNH / 32;
   const EpiDev& e = p.epi;
   const int r = q * 32 + lane;
   const float invN = 1.f / (float)p.N;
@@ -597,40 +609,37 @@ __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo
     return s;
   };
   // ---- accumulator -> registers (columns >= N stay zero and are excluded from every statistic)
-  const bool h0 = n0 < p.N, h1 = n0 + 32 < p.N;
-  float v[64];
+  bool hv[NG];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) v[j] = 0.f;
-  if (h0) { load32(0, v); wait32(v); }
-  if (h1) { load32(32, v + 32); wait32(v + 32); }
+  for (int g = 0; g < NG; ++g) hv[g] = n0 + 32 * g < p.N;
+  float v[BNH];
+#pragma unroll
+  for (int j = 0; j < BNH; ++j) v[j] = 0.f;
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+    if (hv[g]) { load32(32 * g, v + 32 * g); wait32(v + 32 * g); }
   release();                                // the MMA warp may overwrite this accumulator stage
-  if (h0) epi_math32(e, n0, v);
-  if (h1) epi_math32(e, n0 + 32, v + 32);
+#pragma unroll
+  for (int g = 0; g < NG; ++g)
+    if (hv[g]) epi_math32(e, n0 + 32 * g, v + 32 * g);
   // ---- norm1: two-pass LayerNorm on the fp32 values
   if (e.norm1) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) s += v[j];
-    const float mean = exchange(0, s, 0.f).x * invN;
+    const float mean = exchange(0, sum4<BNH>([&](int j) { return v[j]; }), 0.f).x * invN;
     float vs = 0.f;
-    if (h0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; vs += d * d; }
-    }
-    if (h1) {
-#pragma unroll
-      for (int j = 32; j < 64; ++j) { const float d = v[j] - mean; vs += d * d; }
-    }
+    for (int g = 0; g < NG; ++g)
+      if (hv[g]) vs += sum4<32>([&](int j) { const float d = v[32 * g + j] - mean; return d * d; });
     const float rstd = rsqrtf(exchange(1, vs, 0.f).x * invN + 1e-5f);
+    const float nmr = -mean * rstd;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      if (hh == 0 ? h0 : h1) {
+    for (int g = 0; g < NG; ++g) {
+      if (hv[g]) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm1_g + n0 + 32 * hh + j));
-          float* w = v + 32 * hh + j;
-          w[0] = (w[0] - mean) * rstd * g4.x; w[1] = (w[1] - mean) * rstd * g4.y;
-          w[2] = (w[2] - mean) * rstd * g4.z; w[3] = (w[3] - mean) * rstd * g4.w;
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm1_g + n0 + 32 * g + j));
+          float* w = v + 32 * g + j;
+          w[0] = fmaf(w[0], rstd, nmr) * g4.x; w[1] = fmaf(w[1], rstd, nmr) * g4.y;
+          w[2] = fmaf(w[2], rstd, nmr) * g4.z; w[3] = fmaf(w[3], rstd, nmr) * g4.w;
         }
       }
     }
@@ -639,27 +648,30 @@ __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo
   if (e.residual != nullptr && ri.valid) {
     const __nv_bfloat16* rrow = e.residual + ri.row * (long long)e.ldr + n0;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      if (hh == 0 ? h0 : h1) {
+    for (int g = 0; g < NG; ++g) {
+      if (hv[g]) {
+        uint4 u[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
+        for (int t = 0; t < 4; ++t) u[t] = *reinterpret_cast<const uint4*>(rrow + 32 * g + 8 * t);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
           float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(rrow + 32 * hh + j), f);
+          unpack8(u[t], f);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[32 * hh + j + t] += f[t];
+          for (int i = 0; i < 8; ++i) v[32 * g + 8 * t + i] += f[i];
         }
       }
     }
   }
   if (e.out != nullptr) {
-    if (h0) { stage32(v, stage, lane); flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n0, stage, meta, lane); }
-    if (h1) { stage32(v + 32, stage, lane); flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n0 + 32, stage, meta, lane); }
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+      if (hv[g]) { stage32(v + 32 * g, stage, lane); flush32_to(reinterpret_cast<__nv_bfloat16*>(e.out), e.ldc, p, ri, n0 + 32 * g, stage, meta, lane); }
   }
   if (!e.norm2) return;
   // ---- norm2 on w (fp32): LayerNorm (var = E[w^2] - mean^2) or RMSNorm -> FiLM -> SiLU
-  float s = 0.f, ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { s += v[j]; ss += v[j] * v[j]; }
+  const float s = e.norm2 == 1 ? sum4<BNH>([&](int j) { return v[j]; }) : 0.f;
+  const float ss = sum4<BNH>([&](int j) { return v[j] * v[j]; });
   const float2 t = exchange(2, s, ss);
   float m2 = 0.f, k2;
   if (e.norm2 == 1) {
@@ -668,18 +680,19 @@ __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo
   } else {
     k2 = 1.f / fmaxf(sqrtf(t.y), 1e-12f);
   }
+  const float nm2 = -m2 * k2;
   const float* film = nullptr;
   if (e.norm2 == 2 && e.film != nullptr && ri.valid) film = e.film + (long long)((unsigned)ri.row / (unsigned)e.rows_per_sample) * e.film_ld;
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    if (hh == 0 ? h0 : h1) {
-      float* w = v + 32 * hh;
-      const int n = n0 + 32 * hh;
+  for (int g = 0; g < NG; ++g) {
+    if (hv[g]) {
+      float* w = v + 32 * g;
+      const int n = n0 + 32 * g;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm2_g + n + j));
-        w[j] = (w[j] - m2) * k2 * g4.x; w[j + 1] = (w[j + 1] - m2) * k2 * g4.y;
-        w[j + 2] = (w[j + 2] - m2) * k2 * g4.z; w[j + 3] = (w[j + 3] - m2) * k2 * g4.w;
+        w[j] = fmaf(w[j], k2, nm2) * g4.x; w[j + 1] = fmaf(w[j + 1], k2, nm2) * g4.y;
+        w[j + 2] = fmaf(w[j + 2], k2, nm2) * g4.z; w[j + 3] = fmaf(w[j + 3], k2, nm2) * g4.w;
       }
       if (e.norm2 == 2) {
         if (film != nullptr) {
@@ -687,8 +700,8 @@ __device__ __forceinline__ void epilogue_norm(const GemmParams& p, const RowInfo
           for (int j = 0; j < 32; j += 4) {
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(film + n + j));
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(film + p.N + n + j));
-            w[j] = w[j] * (s4.x + 1.f) + b4.x; w[j + 1] = w[j + 1] * (s4.y + 1.f) + b4.y;
-            w[j + 2] = w[j + 2] * (s4.z + 1.f) + b4.z; w[j + 3] = w[j + 3] * (s4.w + 1.f) + b4.w;
+            w[j] = fmaf(w[j], s4.x, w[j]) + b4.x; w[j + 1] = fmaf(w[j + 1], s4.y, w[j + 1]) + b4.y;
+            w[j + 2] = fmaf(w[j + 2], s4.z, w[j + 2]) + b4.z; w[j + 3] = fmaf(w[j + 3], s4.w, w[j + 3]) + b4.w;
           }
         }
 #pragma unroll
@@ -715,6 +728,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   constexpr int ACC_COLS = BN < 32 ? 32 : BN;
   constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;   // two accumulator stages (power of two)
 
+  pdl_trigger();   // the next grid may be scheduled; it waits (pdl_wait) for this one to complete before touching memory
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -752,6 +766,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and descriptors are set up: from here on the previous grid's results are read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -845,10 +860,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
       if (!(p.debug & 1)) {
         if constexpr (NORM) {
-          static_assert(STAGED && BNH == 64, "the norm epilogue keeps 64 columns per warp in registers and stores through the staging tiles");
+          static_assert(STAGED && (BNH == 64 || BNH == 32), "the norm epilogue keeps its columns in registers and stores through the staging tiles");
           const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
           float2* xch = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 1024 + NEPI * EPI_STAGE_BYTES);
-          epilogue_norm<HALVES>(p, ri, n0 + half * BNH, stg, stg + 2048u, xch, tile_parity, q, half, lane,
+          epilogue_norm<BNH, HALVES>(p, ri, n0 + half * BNH, stg, stg + 2048u, xch, tile_parity, q, half, lane,
                                 [&](int c, float* v) { tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
                                 [&](float* v) { tmem_wait_regs32(v); },
                                 [&]() {
@@ -1163,8 +1178,7 @@ int launch_tc2(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorM
   B200_SMEM_OPT_IN((conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI, NORM>), smem);
   const long long total = (long long)ntiles * (p.Npad / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = (int)(total < sm_count() ? total : sm_count());   // persistent: one CTA per SM
-  conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI, NORM><<<grid, 64 + 32 * NEPI, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapO, p);
-  B200_LAUNCH_OK();
+  B200_CUDA_OK(b200_launch(conv_gemm_tc_kernel<BN, STAGES, SIMPLE, NEPI, NORM>, dim3(grid), dim3(64 + 32 * NEPI), smem, st, maps[0], maps[1], maps[2], maps[3], mapB, mapO, p));
   return B200_OK;
 }
 
@@ -1443,7 +1457,7 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   if (has_norm) {
     switch (BN) {
       case 64: return launch_tc2<64, 8, true, 4, true>(maps, mapB, mapO, p, ntiles, st);
-      case 128: return launch_tc2<128, 5, true, 8, true>(maps, mapB, mapO, p, ntiles, st);
+      case 128: return launch_tc2<128, 5, true, 16, true>(maps, mapB, mapO, p, ntiles, st);
       default: return launch_tc2<256, 3, true, 16, true>(maps, mapB, mapO, p, ntiles, st);
     }
   }

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(SMP_THREADS) ddpm_step_kernel(float* __restric
                                                                 const float* __restrict__ noise, const b200_ddpm_coef* __restrict__ coefs,
                                                                 int* __restrict__ slots, int R, int B, long long chw, float cond_scale,
                                                                 int objective, Quant q, float* __restrict__ x_start_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smp_cache[];
   __shared__ unsigned sh_hist[256 + 40];
   const int b = blockIdx.x;
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(SMP_THREADS) edm_phase_kernel(int phase, float
                                                                 const b200_edm_coef* __restrict__ coefs, int* __restrict__ step_ctr,
                                                                 int* __restrict__ slots, int R, int B, long long chw, float cond_scale, Quant q,
                                                                 float* __restrict__ denoised_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float smp_cache[];
   __shared__ unsigned sh_hist[256 + 40];
   const int b = blockIdx.x;
@@ -283,7 +287,7 @@ extern "C" int b200_ddpm_step_sc(float* x, const float* pred, const float* noise
   Quant q{q_lo, q_hi, q_w, thresholding};
   const int smem = smp_smem(chw);
   B200_SMEM_OPT_IN(ddpm_step_kernel, SMP_CACHE_FLOATS * 4);   // dynamic cache + 1.2 KB static histogram exceeds the 48 KB default already at 3x64x64
-  ddpm_step_kernel<<<B, SMP_THREADS, smem, st>>>(x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q, x_start_out);
+  B200_CUDA_OK(b200_launch(ddpm_step_kernel, dim3(B), dim3(SMP_THREADS), smem, st, x, pred, noise, coefs, slots, R, B, chw, cond_scale, objective, q, x_start_out));
   B200_LAUNCH_OK();
   return B200_OK;
 }
