@@ -7,6 +7,8 @@ from .unet import Unet, NullUnet, BaseUnet64, SRUnet256, SRUnet1024, UnetPlan
 from .imagen import Imagen, GaussianDiffusionContinuousTimes
 from .elucidated import ElucidatedImagen
 from .dist import sample_sharded, sample_in_chunks
+from .trainer import TrainedSampler, split_trainer_checkpoint
+from . import t5
 from ._lib import B200Error, LIB_PATH
 
 __version__ = '0.1.0'

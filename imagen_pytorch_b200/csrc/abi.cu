@@ -15,7 +15,7 @@ void b200_set_error(const char* fmt, ...) {
 bool b200_pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("B200_IMAGEN_PDL");
-    return e == nullptr || atoi(e) != 0;
+    return e != nullptr && atoi(e) != 0;   // off by default: measured no gain inside the captured step graph (profiles/r02_pdl_ab.txt)
   }();
   return on;
 }

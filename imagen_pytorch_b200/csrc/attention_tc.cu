@@ -539,6 +539,33 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 constexpr int PT_STAGES = 5;
 constexpr int PT_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 256 + 2048;   // + barriers + row-sum exchange
 
+// 32 scores -> 16 packed bf16x2 probabilities + row-sum contribution.  MODE bit 0: no "- C" (P = exp2(S) directly: the bound only
+// has to keep 2^C * n_keys inside fp32, and O / l is invariant to the common factor 2^C -- one FADD less per score); bits 1-2 are
+// bottleneck experiments of tools/sweep_attention.py (WRONG results): 2 = no MUFU (the score is copied), 4 = no TMEM read.
+// RAGGED is a separate instantiation: the key-bound compare + select per score (ISETP + FSEL) used to run for EVERY tile.
+template <int POLY, int MODE, bool RAGGED>
+__device__ __forceinline__ void pt_chunk32(const uint32_t* sr, float C, int key_base, int n_keys, uint32_t* pk, float& l) {
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float x0 = __uint_as_float(sr[i]), x1 = __uint_as_float(sr[i + 1]);
+    if (!(MODE & 1)) { x0 -= C; x1 -= C; }
+    float p0, p1;
+    if (MODE & 2) { p0 = x0; p1 = x1; }
+    else {
+      p0 = (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) ? ex2_poly(x0) : ex2_approx(x0);
+      p1 = (POLY > 0 && ((i + 1) % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) ? ex2_poly(x1) : ex2_approx(x1);
+    }
+    if (RAGGED) {
+      if (key_base + i >= n_keys) p0 = 0.f;
+      if (key_base + i + 1 >= n_keys) p1 = 0.f;
+    }
+    l0 += p0; l1 += p1;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  l += l0 + l1;
+}
+
 template <int POLY>
 __device__ __forceinline__ bool pt_use_poly(int idx) { return POLY > 0 && (idx % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1; }
 
@@ -546,7 +573,7 @@ __device__ __forceinline__ bool pt_use_poly(int idx) { return POLY > 0 && (idx %
 // softmax pipelines lock IN phase: both exponentiate at the same time at half speed each, then both wait for their next S tile with
 // the MUFU pipe idle (measured: XU pipe 62% busy at 16/clk/SM peak).  With the token, group B's TMEM reads / barrier round trips /
 // S MMA latency run under group A's exponentials and vice versa.
-template <int POLY, int SUB, bool ORDER>   // POLY: every POLY-th exponential on the FMA pipe (0 = all MUFU); SUB: softmax warps per lane quarter per group
+template <int POLY, int SUB, bool ORDER, int MODE>   // POLY: every POLY-th exponential on the FMA pipe (0 = all MUFU); SUB: softmax warps per lane quarter per group; MODE: pt_chunk32
 __global__ void __launch_bounds__(128 + 256 * SUB, 1)
 flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
@@ -700,9 +727,14 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += CH) {
           uint32_t sr[CH];
+          if (MODE & 4) {
 #pragma unroll
-          for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
-          tmem_ld_wait();
+            for (int i = 0; i < CH; ++i) sr[i] = __float_as_uint(-1.f - (float)(lane + i));
+          } else {
+#pragma unroll
+            for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
+            tmem_ld_wait();
+          }
 #pragma unroll
           for (int i = 0; i < CH; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
           if (c0 + CH == 64 && (SUB == 2 || hh == 1 || last_dead)) {
@@ -720,19 +752,9 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
           for (int t = 0; t < CH / 32; ++t) {
             uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const int e = 32 * t + i;
-              const float x0 = __uint_as_float(sr[e]) - C, x1 = __uint_as_float(sr[e + 1]) - C;
-              float p0 = pt_use_poly<POLY>(e) ? ex2_poly(x0) : ex2_approx(x0);
-              float p1 = pt_use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2_approx(x1);
-              if (ragged) {
-                if (key0 + hf * 64 + c0 + e >= p.n_keys) p0 = 0.f;
-                if (key0 + hf * 64 + c0 + e + 1 >= p.n_keys) p1 = 0.f;
-              }
-              l += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
+            const int kb = key0 + hf * 64 + c0 + 32 * t;
+            if (ragged) pt_chunk32<POLY, MODE, true>(sr + 32 * t, C, kb, p.n_keys, pk, l);
+            else pt_chunk32<POLY, MODE, false>(sr + 32 * t, C, kb, p.n_keys, pk, l);
             tmem_st16(p_col + (uint32_t)((c0 + 32 * t) >> 1), pk);
           }
         }
@@ -860,24 +882,25 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
     case 12: PP_LAUNCH(0, 2); break;   // ping-pong, 16 softmax warps (column halves)
     case 13: PP_LAUNCH(4, 2); break;   // ... + 1/4 polynomial exp2
-#define PT_LAUNCH(POLY, SUB, ORDER)                                                                                              \
+#define PT_LAUNCH(POLY, SUB, ORDER, MODE)                                                                                        \
   {                                                                                                                                \
-    B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB, ORDER>), PT_SMEM);                                                           \
+    B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB, ORDER, MODE>), PT_SMEM);                                                     \
     dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
-    B200_CUDA_OK(b200_launch(flash_attn_pt_kernel<POLY, SUB, ORDER>, grid2, dim3(128 + 256 * SUB), PT_SMEM, st, mq, mk, mv, p));    \
+    B200_CUDA_OK(b200_launch(flash_attn_pt_kernel<POLY, SUB, ORDER, MODE>, grid2, dim3(128 + 256 * SUB), PT_SMEM, st, mq, mk, mv, p)); \
   }
-    case 20: PT_LAUNCH(0, 2, false); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
-    case 21: PT_LAUNCH(8, 2, false); break;   // ... + 1/8 of the exponentials on the FMA pipe
-    case 23: PT_LAUNCH(4, 2, false); break;   // ... + 1/4
-    case 26: PT_LAUNCH(0, 1, false); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
-    case 27: PT_LAUNCH(4, 1, false); break;
-    case 30: PT_LAUNCH(0, 2, true); break;    // + MUFU token between the two groups
-    case 31: PT_LAUNCH(8, 2, true); break;
-    case 32: PT_LAUNCH(5, 2, true); break;
-    case 33: PT_LAUNCH(4, 2, true); break;
-    case 34: PT_LAUNCH(3, 2, true); break;
-    case 36: PT_LAUNCH(0, 1, true); break;
-    case 37: PT_LAUNCH(4, 1, true); break;
+    case 20: PT_LAUNCH(0, 2, false, 0); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
+    case 23: PT_LAUNCH(4, 2, false, 0); break;   // ... + 1/4 of the exponentials on the FMA pipe
+    case 26: PT_LAUNCH(0, 1, false, 0); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
+    case 30: PT_LAUNCH(0, 2, true, 0); break;    // + MUFU token between the two groups (slower: profiles/r02_attention_variant_sweep.txt)
+    case 40: PT_LAUNCH(0, 2, false, 1); break;   // P = exp2(S) without the "- C" (one FADD less per score)
+    case 41: PT_LAUNCH(8, 2, false, 1); break;
+    case 42: PT_LAUNCH(4, 2, false, 1); break;
+    case 43: PT_LAUNCH(3, 2, false, 1); break;
+    case 46: PT_LAUNCH(0, 1, false, 1); break;
+    case 47: PT_LAUNCH(4, 1, false, 1); break;
+    case 50: PT_LAUNCH(0, 2, false, 3); break;   // bottleneck experiment: no MUFU
+    case 51: PT_LAUNCH(0, 2, false, 5); break;   // bottleneck experiment: no TMEM reads
+    case 52: PT_LAUNCH(0, 2, false, 7); break;   // bottleneck experiment: neither
 #undef PT_LAUNCH
     default: PP_LAUNCH(0, 1); break;   // ping-pong: two query tiles per CTA, all exponentials on MUFU
 #undef PP_LAUNCH

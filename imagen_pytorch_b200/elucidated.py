@@ -231,6 +231,7 @@ class ElucidatedImagen(_SamplerBase):
         try:
             device = default(device, self.device)
             self.reset_unets_all_one_device(device=device)
+            text_embeds, text_masks = self._encode_texts(texts, text_embeds, text_masks, device)   # elucidated_imagen.py:583-589
             if exists(cond_images) and cond_images.dtype == torch.uint8:      # cast_uint8_images_to_float (elucidated_imagen.py:581)
                 cond_images = cond_images / 255
             self._check_cond_images(cond_images, start_at_unet_number, stop_at_unet_number)

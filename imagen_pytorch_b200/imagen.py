@@ -13,6 +13,7 @@ from __future__ import annotations
 import math
 import os
 from contextlib import nullcontext
+from functools import partial
 
 import torch
 import torch.nn.functional as F
@@ -23,17 +24,7 @@ from . import _lib
 from .params import cast_tuple
 from .unet import Unet, NullUnet
 
-T5_DIMS = {'t5-small': 512, 't5-base': 768, 't5-large': 1024, 't5-3b': 1024, 't5-11b': 1024,
-           'google/t5-v1_1-small': 512, 'google/t5-v1_1-base': 768, 'google/t5-v1_1-large': 1024,
-           'google/t5-v1_1-xl': 2048, 'google/t5-v1_1-xxl': 4096}
-DEFAULT_T5_NAME = 'google/t5-v1_1-base'
-
-
-def get_encoded_dim(name):
-    """Hidden size of the T5 encoder `name` (the reference reads it from the HF config, t5.py:47-58)."""
-    if name not in T5_DIMS:
-        raise ValueError(f'unknown text encoder {name!r}: pass text_embed_dim explicitly')
-    return T5_DIMS[name]
+from .t5 import DEFAULT_T5_NAME, get_encoded_dim, t5_encode_text, TextEmbedCache   # noqa: E402  (reference: imagen_pytorch.py:23)
 
 
 def exists(v):
@@ -163,6 +154,7 @@ class _SamplerBase(nn.Module):
         self.lowres_noise_schedule = GaussianDiffusionContinuousTimes(noise_schedule=lowres_noise_schedule)
         self.text_encoder_name = text_encoder_name
         self.text_embed_dim = default(text_embed_dim, lambda: get_encoded_dim(text_encoder_name))
+        self.encode_text = partial(t5_encode_text, name=text_encoder_name)    # :1884; replaceable (e.g. enable_text_embed_cache)
         self.unets = nn.ModuleList([])
         for ind, one_unet in enumerate(unets):
             assert isinstance(one_unet, (Unet, NullUnet))
@@ -197,6 +189,20 @@ class _SamplerBase(nn.Module):
     def device(self):
         return self._temp.device
 
+    def enable_text_embed_cache(self, capacity=4096):
+        """Route sample(texts=...) through an LRU of per-prompt embeddings (t5.TextEmbedCache): repeated prompts skip the encoder."""
+        self.text_embed_cache = TextEmbedCache(capacity, encode_fn=self.encode_text)
+        self.encode_text = partial(self.text_embed_cache.encode, name=self.text_encoder_name)
+        return self.text_embed_cache
+
+    def _encode_texts(self, texts, text_embeds, text_masks, device):
+        """texts -> (text_embeds, text_masks) when no embeddings were passed (imagen_pytorch.py:2326-2332)."""
+        if exists(texts) and not exists(text_embeds) and not self.unconditional:
+            assert all([*map(len, texts)]), 'text cannot be empty'
+            text_embeds, text_masks = self.encode_text(texts, return_attn_mask=True)
+            text_embeds, text_masks = text_embeds.to(device), text_masks.to(device)
+        return text_embeds, text_masks
+
     def force_unconditional_(self):
         self.condition_on_text = False
         self.unconditional = True
@@ -217,8 +223,6 @@ class _SamplerBase(nn.Module):
         for name, val in unsupported.items():
             if exists(val):
                 raise NotImplementedError(f'sample({name}=...) is outside the B200 sampling hot path (see DESIGN.md)')
-        if exists(texts) and not exists(text_embeds) and not self.unconditional:
-            raise NotImplementedError('the T5 text encoder is out of scope: pass text_embeds= (and optionally text_masks=)')
         if not self.unconditional:
             assert exists(text_embeds), 'text must be passed in if the network was not trained without text `condition_on_text` must be set to `False` when training'
         assert not (self.condition_on_text and not exists(text_embeds)), 'text or text encodings must be passed into imagen if specified'
@@ -435,6 +439,7 @@ class Imagen(_SamplerBase):
         options = dict(options or {})
         device = default(device, self.device)
         self.reset_unets_all_one_device(device=device)
+        text_embeds, text_masks = self._encode_texts(texts, text_embeds, text_masks, device)
         cond_images = options.get('cond_images')
         if exists(cond_images) and cond_images.dtype == torch.uint8:          # cast_uint8_images_to_float (:91-94, :2324)
             cond_images = cond_images / 255

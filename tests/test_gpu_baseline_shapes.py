@@ -196,6 +196,54 @@ def test_dim_head_32_and_cond_images_forward_and_sample():
         im.sample(text_embeds=g['text_embeds'].to(DEV), cond_scale=1., use_tqdm=False)
 
 
+# ------------------------------------------------------------------------------------------------ callers either side of the path
+
+def test_sample_from_texts_and_trainer_checkpoint_with_ema():
+    """sample(texts=...) through the encode_text hook equals sample(text_embeds=...) of the same encoder output; a TrainedSampler loaded
+    from an ImagenTrainer.save-layout checkpoint samples with the EMA weights (chunked by max_batch_size) unless use_non_ema."""
+    from tests.helpers import synth_weights
+    from tests.test_host_logic import _ToyTokenizer, _toy_t5
+    from imagen_pytorch_b200 import t5, TrainedSampler
+    g = load_golden('unet_base_dim32.pt')
+    sd_online, sd_ema = synth_weights('test_base', 1), synth_weights('test_base', 2)
+    t5.register_text_encoder('toy-t5', _toy_t5(), _ToyTokenizer())
+
+    def imagen_with(sd):
+        u = b2.Unet(**g['kwargs'])
+        u.load_state_dict(sd)
+        return b2.Imagen(u.to(DEV), image_sizes=32, timesteps=3, text_encoder_name='toy-t5').to(DEV)
+
+    im = imagen_with(sd_online)
+    assert im.text_embed_dim == 64
+    texts = ['a cat', 'a dog on a skateboard', 'nothing']
+    torch.manual_seed(11)
+    a = im.sample(texts=texts, cond_scale=2., use_tqdm=False)
+    emb, mask = t5.t5_encode_text(texts, name='toy-t5', return_attn_mask=True)
+    torch.manual_seed(11)
+    b = im.sample(text_embeds=emb, text_masks=mask, cond_scale=2., use_tqdm=False)
+    assert a.shape == (3, 3, 32, 32) and torch.equal(a, b)
+    ckpt = dict(model={'unets.0.' + k: v for k, v in sd_online.items()}, ema={'0.ema_model.' + k: v for k, v in sd_ema.items()}, version='1.26.2',
+                steps=torch.tensor([3]))
+    ts = TrainedSampler(imagen_with(synth_weights('test_base', 3)))
+    ts.load(ckpt)
+    torch.manual_seed(12)
+    e = ts.sample(text_embeds=emb[:2], text_masks=mask[:2], cond_scale=2., use_tqdm=False)
+    torch.manual_seed(12)
+    e_ref = imagen_with(sd_ema).sample(text_embeds=emb[:2], text_masks=mask[:2], cond_scale=2., use_tqdm=False)
+    torch.manual_seed(12)
+    o = ts.sample(text_embeds=emb[:2], text_masks=mask[:2], cond_scale=2., use_tqdm=False, use_non_ema=True)
+    torch.manual_seed(12)
+    o_ref = imagen_with(sd_online).sample(text_embeds=emb[:2], text_masks=mask[:2], cond_scale=2., use_tqdm=False)
+    assert torch.equal(e, e_ref) and torch.equal(o, o_ref) and not torch.equal(e, o)
+    # chunked sampling: two chunks of (2, 1) samples, each chunk drawing its own noise in order
+    torch.manual_seed(13)
+    c = ts.sample(text_embeds=emb, text_masks=mask, cond_scale=2., use_tqdm=False, max_batch_size=2)
+    torch.manual_seed(13)
+    c0 = ts.sample(text_embeds=emb[:2], text_masks=mask[:2], cond_scale=2., use_tqdm=False)
+    c1 = ts.sample(text_embeds=emb[2:], text_masks=mask[2:], cond_scale=2., use_tqdm=False)
+    assert c.shape[0] == 3 and torch.equal(c, torch.cat((c0, c1)))
+
+
 # ------------------------------------------------------------------------------------------------ plan cache (ADVICE r01)
 
 def test_plan_and_step_graph_are_reused_across_sample_calls_and_track_weight_updates():

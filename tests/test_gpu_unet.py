@@ -171,9 +171,11 @@ def test_elucidated_cascade_matches_oracle_with_shared_noise():
         ref = sampler_ref.elucidated_sample(models, (16, 32), text_embeds=te, cond_scale=g['cond_scale'],
                                             hparams=dict(num_sample_steps=g['num_sample_steps']), randn=cuda_randn)
     d = (out.cpu() - ref).abs()
-    record('edm_cascade', mean_abs=d.mean(), max_abs=d.max())
-    # sigma_max = 80: the first Heun steps run the untrained net on |x| ~ 80 inputs, which amplifies bf16 noise (measured mean 1.1e-2)
-    assert d.mean() < 3e-2
+    record('edm_cascade', mean_abs=d.mean(), max_abs=d.max(), p999_abs=d.flatten().kthvalue(int(0.999 * d.numel())).values, frac_gt_0p1=(d > 0.1).float().mean())
+    # sigma_max = 80: the first Heun steps run the untrained net on |x| ~ 80 inputs, which amplifies bf16 noise (measured mean 1.1e-2,
+    # max 0.28 on a handful of pixels).  Bounds on the mean AND on the tail: a control-flow error (wrong sigma, missing Heun correction,
+    # wrong thresholding) moves every pixel by O(0.1-1), see the init / inpaint variants below at sigma_max = 2 (max 2e-2).
+    assert d.mean() < 3e-2 and d.max() < 0.6 and (d > 0.1).float().mean() < 2e-2
 
 
 def _cascade_pair(g):
@@ -248,8 +250,9 @@ def test_elucidated_sampler_options_match_oracle_with_shared_noise():
                                               inpaint_masks=g['inpaint_masks'], inpaint_resample_times=g['inpaint_resample_times'],
                                               randn=cuda_randn, **common)
     d = [(a.cpu() - b).abs().mean().item() for a, b in zip(o_init + o_inp, r_init + r_inp)]
-    record('edm_options', init_base=d[0], init_sr=d[1], inpaint_base=d[2], inpaint_sr=d[3])
-    assert max(d) < 3e-2
+    dmax = [(a.cpu() - b).abs().max().item() for a, b in zip(o_init + o_inp, r_init + r_inp)]
+    record('edm_options', init_base=d[0], init_sr=d[1], inpaint_base=d[2], inpaint_sr=d[3], max_abs=max(dmax))
+    assert max(d) < 3e-2 and max(dmax) < 0.25
     m, known = _known_pixels(g)
     assert torch.equal(o_inp[1].cpu()[m], known)
 

@@ -95,8 +95,8 @@ def test_sample_argument_validation_mirrors_reference():
         im.sample(text_embeds=torch.randn(1, 8, 32), use_tqdm=False)          # wrong embedding dim
     with pytest.raises(AssertionError):
         im.sample(use_tqdm=False)                                               # text required
-    with pytest.raises(NotImplementedError):
-        im.sample(texts=['a cat'], use_tqdm=False)                              # T5 encoder out of scope
+    with pytest.raises(AssertionError):
+        im.sample(texts=['a cat', ''], use_tqdm=False)                          # 'text cannot be empty' (:2327)
     with pytest.raises(AssertionError):                                           # cond_images for a U-Net built without cond_images_channels (:1555)
         im.sample(text_embeds=torch.randn(1, 8, 64), cond_images=torch.zeros(1, 3, 16, 16), use_tqdm=False)
     with pytest.raises(NotImplementedError):
@@ -129,3 +129,88 @@ def test_unet_plan_cache_survives_noop_module_moves():
     u._plans['sentinel'] = type('P', (), {'fingerprint': fp})()
     u.to('cpu')                                               # Imagen.sample() calls unets.to(device) on every call
     assert 'sentinel' in u._plans and u._fingerprint() == fp
+
+
+class _ToyTokenizer:
+    """Whitespace tokenizer with the HF batch_encode_plus contract (right padding, 'longest')."""
+
+    def batch_encode_plus(self, texts, return_tensors='pt', padding='longest', max_length=256, truncation=True):
+        ids = [[(hash(w) % 97) + 3 for w in t.split()][:max_length - 1] + [1] for t in texts]      # 1 = </s>
+        n = max(len(i) for i in ids)
+        out = type('Enc', (), {})()
+        out.input_ids = torch.tensor([i + [0] * (n - len(i)) for i in ids])
+        out.attention_mask = torch.tensor([[1] * len(i) + [0] * (n - len(i)) for i in ids])
+        return out
+
+
+def _toy_t5(dim=64):
+    from transformers import T5Config, T5EncoderModel
+    torch.manual_seed(0)
+    return T5EncoderModel(T5Config(vocab_size=100, d_model=dim, d_kv=16, d_ff=128, num_layers=2, num_heads=4)).eval()
+
+
+def test_t5_mirror_masks_padding_and_cache_reproduces_batches():
+    """imagen_pytorch_b200.t5 (mirror of the reference's t5.py): padding embeddings are exactly zero, the mask is the tokenizer's,
+    and the per-prompt LRU returns the same embeddings for a prompt whatever batch it was first encoded in."""
+    from imagen_pytorch_b200 import t5
+    t5.register_text_encoder('toy-t5', _toy_t5(), _ToyTokenizer())
+    assert t5.get_encoded_dim('toy-t5') == 64 and t5.get_encoded_dim('google/t5-v1_1-xl') == 2048
+    texts = ['a photo of a cat', 'dog', 'a very long prompt about nothing in particular']
+    emb, mask = t5.t5_encode_text(texts, name='toy-t5', return_attn_mask=True)
+    emb, mask = emb.cpu(), mask.cpu()
+    assert emb.shape == (3, 9, 64) and mask.dtype == torch.bool and mask.sum(1).tolist() == [6, 2, 9]
+    assert emb[~mask].abs().max() == 0 and emb[mask].abs().min() > 0
+    cache = t5.TextEmbedCache(capacity=8)
+    e1, m1 = cache.encode(texts, name='toy-t5')
+    assert (cache.hits, cache.misses) == (0, 3)
+    assert torch.equal(m1, mask) and torch.allclose(e1, emb, atol=1e-5)
+    e2, m2 = cache.encode(['dog', 'a photo of a cat'], name='toy-t5')           # all hits; different batch => different padded length
+    assert (cache.hits, cache.misses) == (2, 3) and e2.shape == (2, 6, 64)
+    ref, refm = t5.t5_encode_text(['dog', 'a photo of a cat'], name='toy-t5', return_attn_mask=True)
+    assert torch.equal(m2, refm.cpu()) and torch.allclose(e2, ref.cpu(), atol=1e-5)
+
+
+def test_sample_with_texts_goes_through_encode_text_hook():
+    """Imagen.sample(texts=...) encodes through self.encode_text (imagen_pytorch.py:2326-2332) -- here it reaches the device check
+    with text_embeds of the encoder's width; with the cache enabled the second call is served from the LRU."""
+    from imagen_pytorch_b200 import t5, B200Error
+    t5.register_text_encoder('toy-t5', _toy_t5(), _ToyTokenizer())
+    im = Imagen(Unet(dim=32, dim_mults=(1, 2), text_embed_dim=64), image_sizes=16, text_encoder_name='toy-t5', timesteps=2)
+    assert im.text_embed_dim == 64
+    cache = im.enable_text_embed_cache()
+    for _ in range(2):
+        with pytest.raises(B200Error):                                          # CPU box: the sampler refuses to run, after the text was encoded
+            im.sample(texts=['a cat', 'a dog on a skateboard'], use_tqdm=False)
+    assert (cache.hits, cache.misses) == (2, 2)
+
+
+def test_trained_sampler_loads_trainer_checkpoint_and_swaps_ema_unets(tmp_path):
+    """ImagenTrainer.save layout (trainer.py:677-736) -> TrainedSampler.load: online weights into imagen.unets, 'i.ema_model.*' into the EMA
+    twins; sample() runs on the EMA U-Nets unless use_non_ema (trainer.py:846-869, :947-961) and chunks by max_batch_size (:188-206)."""
+    from imagen_pytorch_b200 import TrainedSampler
+    kw = dict(dim=32, dim_mults=(1, 2), text_embed_dim=64)
+    im = Imagen((Unet(**kw), Unet(**kw)), image_sizes=(16, 32), text_embed_dim=64, timesteps=2)
+    sds = [{k: torch.randn_like(v) for k, v in u.state_dict().items()} for u in im.unets]
+    emas = [{k: torch.randn_like(v) for k, v in u.state_dict().items()} for u in im.unets]
+    ckpt = dict(model={f'unets.{i}.{k}': v for i, sd in enumerate(sds) for k, v in sd.items()},
+                ema={**{f'{i}.ema_model.{k}': v for i, sd in enumerate(emas) for k, v in sd.items()},
+                     **{f'{i}.online_model.{k}': v for i, sd in enumerate(sds) for k, v in sd.items()},     # older ema_pytorch versions save these too
+                     '0.initted': torch.tensor([True]), '0.step': torch.tensor([7]), '1.initted': torch.tensor([True]), '1.step': torch.tensor([7])},
+                version='1.26.2', steps=torch.tensor([7, 7]), optim0={'state': {}}, scaler0={})
+    path = tmp_path / 'checkpoint.pt'
+    torch.save(ckpt, path)
+    ts = TrainedSampler(im)
+    steps, version = ts.load(str(path))
+    assert version == '1.26.2' and steps.tolist() == [7, 7]
+    for i in range(2):
+        assert all(torch.equal(im.unets[i].state_dict()[k], sds[i][k]) for k in sds[i])
+        assert all(torch.equal(ts.ema_unets[i].state_dict()[k], emas[i][k]) for k in emas[i])
+    seen = []
+    im.sample = lambda **k: (seen.append((im.unets is ts.ema_unets, k['text_embeds'].shape[0])), torch.zeros(k['text_embeds'].shape[0], 3, 4, 4))[1]
+    out = ts.sample(text_embeds=torch.randn(5, 8, 64), cond_scale=2., max_batch_size=2)
+    assert out.shape[0] == 5 and seen == [(True, 2), (True, 2), (True, 1)] and im.unets is not ts.ema_unets     # swapped in, chunked, restored
+    seen.clear()
+    ts.sample(text_embeds=torch.randn(3, 8, 64), use_non_ema=True)
+    assert seen == [(False, 3)]
+    with pytest.raises(RuntimeError):
+        TrainedSampler(im).load(dict(model=ckpt['model'], version='x'))                 # no EMA weights in the checkpoint
