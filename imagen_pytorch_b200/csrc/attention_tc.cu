@@ -61,6 +61,7 @@ struct FaParams {
   int q_rs, rows, n_keys;
   int q_heads_first, kv_heads_first;   // coordinate order of the (rows, heads) dims in the tensor maps
   float max_logit;
+  uint32_t wait_ns;                    // suspend-time hint of the barrier waits (0 = plain spin); B200_IMAGEN_FA_WAIT_NS
 };
 
 template <int NW, bool PF, bool WA>
@@ -636,7 +637,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % PT_STAGES;
         const uint32_t n = (uint32_t)(j / PT_STAGES);
-        mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
+        mbar_wait_sleep(&kv_empty[st], (n & 1u) ^ 1u, p.wait_ns);
         mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
         uint8_t* dst = sKV + st * FA_KV_BYTES;
         if (p.kv_heads_first) {
@@ -657,8 +658,8 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
       auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
         const int st = j % PT_STAGES;
-        mbar_wait(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1));
-        mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
+        mbar_wait_sleep(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1), p.wait_ns);
+        mbar_wait_sleep(&s_empty[g], (uint32_t)((j & 1) ^ 1), p.wait_ns);
         tc_fence_after();
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
 #pragma unroll
@@ -666,7 +667,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[g]);
       };
-      mbar_wait(q_full, 0);
+      mbar_wait_sleep(q_full, 0, p.wait_ns);
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);
@@ -675,7 +676,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         for (int hf = 0; hf < 2; ++hf) {        // the first 64 keys are multiplied while the second 64 are exponentiated
           if (hf == 1 && dead1 && j == ntiles - 1) break;
           const int pb = 2 * g + hf;
-          mbar_wait(&p_full[pb], (uint32_t)(j & 1));
+          mbar_wait_sleep(&p_full[pb], (uint32_t)(j & 1), p.wait_ns);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -708,13 +709,13 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const uint32_t tok_par = g == 0 ? (uint32_t)((j & 1) ^ 1) : (uint32_t)(j & 1);
       if (SUB == 2 && sub == 1 && last_dead) {          // nothing valid in this warp's half of the last tile: only pass the token on
         if (ORDER) {
-          mbar_wait(&order_bar[g], tok_par);
+          mbar_wait_sleep(&order_bar[g], tok_par, p.wait_ns);
           __syncwarp();
           if (lane == 0) mbar_arrive(&order_bar[g ^ 1]);
         }
         break;
       }
-      mbar_wait(&s_full[g], (uint32_t)(j & 1));
+      mbar_wait_sleep(&s_full[g], (uint32_t)(j & 1), p.wait_ns);
       tc_fence_after();
       bool have_token = !ORDER;
       constexpr int CH = SUB == 2 ? 32 : 64;
@@ -742,11 +743,11 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             mbar_arrive(&s_empty[g]);           // this thread's share of S_g is in registers
           }
           if (c0 == 0) {
-            mbar_wait(&p_empty[pb], (uint32_t)((j & 1) ^ 1));   // the P V MMAs of tile j-1 have finished reading this half of P
+            mbar_wait_sleep(&p_empty[pb], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // the P V MMAs of tile j-1 have finished reading this half of P
             tc_fence_after();
           }
           if (!have_token) {                    // scores are in registers: now wait for this group's turn on the MUFU pipe
-            mbar_wait(&order_bar[g], tok_par);
+            mbar_wait_sleep(&order_bar[g], tok_par, p.wait_ns);
             have_token = true;
           }
 #pragma unroll
@@ -768,7 +769,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
     // ---- O / l -> global (with SUB == 2 the two column-half threads of a row add their sums and each stores 32 channels)
-    mbar_wait(&o_full[g], 0);
+    mbar_wait_sleep(&o_full[g], 0, p.wait_ns);
     tc_fence_after();
     if (SUB == 2) {
       float* sLg = sL + g * 2 * FA_BM;
@@ -849,6 +850,10 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.q_bs = q_bs; p.q_hs = q_hs; p.q_rs = q_rs; p.rows = rows; p.n_keys = n_keys; p.max_logit = max_logit;
   p.q_heads_first = q_hf ? 1 : 0; p.kv_heads_first = kv_hf ? 1 : 0;
+  {
+    static const uint32_t wns = [] { const char* ev = getenv("B200_IMAGEN_FA_WAIT_NS"); return (uint32_t)(ev ? atoi(ev) : 0); }();
+    p.wait_ns = wns;
+  }
   dim3 grid((rows + FA_BM - 1) / FA_BM, n_heads, B);
   // kernel variant: (softmax warps, S prefetch, warp-level barrier arrive).  Default chosen from B200 measurements
   // (profiles/); B200_IMAGEN_FA_VARIANT overrides it for the tuning sweep in tools/sweep_attention.py.
@@ -898,6 +903,11 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 43: PT_LAUNCH(3, 2, false, 1); break;
     case 46: PT_LAUNCH(0, 1, false, 1); break;
     case 47: PT_LAUNCH(4, 1, false, 1); break;
+    case 39: PT_LAUNCH(2, 1, false, 1); break;
+    case 48: PT_LAUNCH(3, 1, false, 1); break;
+    case 49: PT_LAUNCH(5, 1, false, 1); break;
+    case 44: PT_LAUNCH(6, 1, false, 1); break;
+    case 45: PT_LAUNCH(8, 1, false, 1); break;
     case 50: PT_LAUNCH(0, 2, false, 3); break;   // bottleneck experiment: no MUFU
     case 51: PT_LAUNCH(0, 2, false, 5); break;   // bottleneck experiment: no TMEM reads
     case 52: PT_LAUNCH(0, 2, false, 7); break;   // bottleneck experiment: neither

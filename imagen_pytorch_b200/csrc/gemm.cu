@@ -1060,6 +1060,239 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------ tcgen05 kernel, transposed (<= 128 output channels)
+// For layers with <= 128 output channels the M128 x N128 MMA of the kernel above is the bottleneck: every K=16 instruction reads 4 KB of A
+// and 4 KB of B from shared memory for 64 cycles of math and the two do not overlap (878 TFLOP/s issue-only, vs 1398 for N = 256;
+// profiles/r01_gemm_bottleneck.txt), and per 128 x 128 tile the CTA pulls 32 KB of operands through L2 per 2.1 MFLOP.  This kernel computes
+// the TRANSPOSED product  D^T[c][pixel] = sum_k W[c][k] * X[pixel][k]:  the weights are the M = 128 operand, a tile of 256 output pixels is the
+// N = 256 operand (same shared-memory layouts, roles swapped), i.e. the instruction shape and operand traffic of the 256-wide tiles.
+// The accumulator then holds channels in TMEM lanes and pixels in columns, so the epilogue transposes through shared memory:
+//   phase A (thread = channel): tcgen05.ld 16 pixels -> + bias, activation -> fp32 staging tile [16 pixels][128 channels] (conflict-free pitch)
+//   phase B (8 threads = one pixel row, 16 channels each): + residual -> raw bf16 row store and / or row statistics (shuffles over the 8
+//            lanes) -> LayerNorm | RMSNorm * FiLM -> SiLU -> bf16 row store: every store instruction writes whole 256-byte pixel rows.
+// Two groups of four epilogue warps (one per TMEM lane quarter) each own 128 of the tile's 256 pixels.
+constexpr int T_BP = 256;                               // pixels per tile (MMA N)
+constexpr int T_W_BYTES = 128 * BK * 2;                 // weight tile (MMA A operand): 16 KB
+constexpr int T_X_BYTES = T_BP * BK * 2;                // pixel tile (MMA B operand): 32 KB
+constexpr int T_STAGE_BYTES = T_W_BYTES + T_X_BYTES;
+constexpr int T_STG_PITCH = 144;                        // floats per staged pixel row: 128 channels, +4 per 32-channel block, +12 pad (bank-conflict free)
+constexpr int T_STG_BYTES = 16 * T_STG_PITCH * 4;       // per group: 16 pixel rows
+
+__device__ __forceinline__ int t_stg_col(int c) { return c + 4 * (c >> 5); }
+
+template <int STAGES>
+__global__ void __launch_bounds__(64 + 256, 1)
+conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                     const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ GemmParams p) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * T_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * T_STAGE_BYTES + 1024);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.ntiles_m;               // 256-pixel tiles; one channel tile (Npad == 128)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.nchunks[1] > 0) tma_prefetch_desc(&mapA1);
+    if (p.nchunks[2] > 0) tma_prefetch_desc(&mapA2);
+    if (p.nchunks[3] > 0) tma_prefetch_desc(&mapA3);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 8);             // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);        // two accumulator stages of 256 pixel columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: weight tile {64 k, 128 channels} + pixel tile {64 ch, bw, bh, bb} shifted by the tap
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int wblk = tile % p.tiles_w;
+        const int hblk = (tile / p.tiles_w) % p.tiles_h;
+        const int bblk = tile / (p.tiles_w * p.tiles_h);
+        const int w0 = wblk * p.bw, h0 = hblk * p.bh, b0 = bblk * p.bb;
+        int kc = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int src = p.seg[s].src;
+          const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : (src == 2 ? &mapA2 : &mapA3));
+          const int dh = p.seg[s].dh, dw = p.seg[s].dw;
+          const int nch = p.nchunks[src];
+          for (int cc = 0; cc < nch; ++cc, ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], T_STAGE_BYTES);
+            uint8_t* sW = smem + stage * T_STAGE_BYTES;
+            tma_load_2d(sW, &mapW, &full_bar[stage], kc * BK, 0);
+            tma_load_4d(sW + T_W_BYTES, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer: M = 128 (channels), N = 256 (pixels), both operands K-major
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_BP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T_BP);
+        for (int kc = 0; kc < p.total_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(smem + stage * T_STAGE_BYTES);
+          const uint64_t adesc = make_sw128_kmajor_desc(w_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(w_addr + T_W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------- epilogue: q = TMEM lane quarter (channels 32q..32q+31), grp = pixel half of the tile
+    const EpiDev& e = p.epi;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int c_lane = q * 32 + lane;                  // phase A: this thread's channel
+    const int t = q * 32 + lane;                       // phase B: thread index inside the group
+    const int prow = t >> 3, cs = t & 7;               //          pixel row of the 16-row chunk, 16-channel slice
+    const int c0 = cs * 16;
+    const bool cvalid = c0 < p.N;
+    float* stg = stg_all + grp * (T_STG_BYTES / 4);
+    const float bias = (e.bias != nullptr) ? __ldg(e.bias + c_lane) : 0.f;   // padded to Npad by the caller
+    const float invN = 1.f / (float)p.N;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T_BP + grp * 128);
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        // ---- phase A: 16 pixels of this thread's channel -> staging (transposed)
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)(16 * ch), v);
+        if (ch == 7) {                                 // the accumulator stage is in registers / shared memory: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int col = t_stg_col(c_lane);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float y = v[i] + bias;
+          if (e.act == B200_ACT_SILU) y = silu_f(y);
+          else if (e.act == B200_ACT_GELU) y = gelu_erf_f(y);
+          stg[i * T_STG_PITCH + col] = y * e.out_scale;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(8 + grp) : "memory");
+        // ---- phase B: one pixel row x 16 channels per thread
+        const RowInfo ri = tile_row(p, tile, row_in_tile(p, grp * 128 + ch * 16 + prow));
+        float f[16];
+        {
+          const float4* src = reinterpret_cast<const float4*>(stg + prow * T_STG_PITCH + t_stg_col(c0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 x4 = src[k];
+            f[4 * k] = x4.x; f[4 * k + 1] = x4.y; f[4 * k + 2] = x4.z; f[4 * k + 3] = x4.w;
+          }
+        }
+        const bool live = ri.valid && cvalid;
+        if (live && e.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(e.residual + ri.row * (long long)e.ldr + c0);
+          float g[8];
+          unpack8(rp[0], g);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] += g[k];
+          unpack8(rp[1], g);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[8 + k] += g[k];
+        }
+        if (live && e.out != nullptr) {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + ri.row * (long long)e.ldc + c0);
+          op[0] = pack8(f);
+          op[1] = pack8(f + 8);
+        }
+        if (e.norm2) {
+          float s = 0.f, ss = 0.f;
+          if (cvalid) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s += f[k]; ss += f[k] * f[k]; }
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {            // the 8 threads of a pixel row are 8 consecutive lanes
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          }
+          float m2 = 0.f, k2;
+          if (e.norm2 == 1) {
+            m2 = s * invN;
+            k2 = rsqrtf(fmaxf(ss * invN - m2 * m2, 0.f) + 1e-5f);
+          } else {
+            k2 = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          }
+          if (live) {
+            const float nm2 = -m2 * k2;
+            const float* film = (e.norm2 == 2 && e.film != nullptr) ? e.film + (long long)((unsigned)ri.row / (unsigned)e.rows_per_sample) * e.film_ld : nullptr;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.norm2_g + c0 + k));
+              f[k] = fmaf(f[k], k2, nm2) * g4.x; f[k + 1] = fmaf(f[k + 1], k2, nm2) * g4.y;
+              f[k + 2] = fmaf(f[k + 2], k2, nm2) * g4.z; f[k + 3] = fmaf(f[k + 3], k2, nm2) * g4.w;
+              if (film != nullptr) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(film + c0 + k));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(film + p.N + c0 + k));
+                f[k] = fmaf(f[k], s4.x, f[k]) + b4.x; f[k + 1] = fmaf(f[k + 1], s4.y, f[k + 1]) + b4.y;
+                f[k + 2] = fmaf(f[k + 2], s4.z, f[k + 2]) + b4.z; f[k + 3] = fmaf(f[k + 3], s4.w, f[k + 3]) + b4.w;
+              }
+            }
+            if (e.norm2 == 2) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] = silu_f(f[k]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out_norm) + ri.row * (long long)e.ld_norm + c0);
+            op[0] = pack8(f);
+            op[1] = pack8(f + 8);
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(8 + grp) : "memory");   // the staging tile may be overwritten
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ SIMT checker
 
 struct RefSrc {
@@ -1372,6 +1605,63 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   // ---- tensor maps
   EncodeTiledFn enc = get_encode_fn();
   B200_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled not available from the driver");
+  // ---- transposed kernel for MMA-bound layers with <= 128 output channels (see conv_gemm_tcT_kernel)
+  {
+    static const bool t_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_T"); return ev == nullptr || atoi(ev) != 0; }();
+    const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const long long Mll = (long long)B * H * W;
+    const bool t_epi = e.out_mode == B200_OUT_BF16 && e.split_col == 0 && e.rows_per_group == 0 && e.l2_cols == 0 && e.dup_rows == 0 && e.norm1 == 0 &&
+                       (N & 15) == 0 && (e.out == nullptr || ((e.ldc & 7) == 0 && al16(e.out))) && (e.out != nullptr || e.norm2 != 0) &&
+                       (e.residual == nullptr || ((e.ldr & 7) == 0 && al16(e.residual))) && (e.norm2 == 0 || (al16(e.out_norm) && (e.ld_norm & 7) == 0)) &&
+                       Mll < (1ll << 31);
+    if (t_on && p.Npad == 128 && t_epi && total >= 8 && Mll >= (long long)T_BP * sm_count()) {   // at least one 256-pixel tile per SM
+      GemmParams pt = p;
+      pt.bw = W >= T_BP ? T_BP : next_pow2(W);
+      pt.bh = next_pow2(H) < T_BP / pt.bw ? next_pow2(H) : T_BP / pt.bw;
+      pt.bb = T_BP / (pt.bw * pt.bh);
+      for (pt.lbw = 0; (1 << pt.lbw) < pt.bw; ++pt.lbw) {}
+      for (pt.lbh = 0; (1 << pt.lbh) < pt.bh; ++pt.lbh) {}
+      pt.tiles_w = (W + pt.bw - 1) / pt.bw;
+      pt.tiles_h = (H + pt.bh - 1) / pt.bh;
+      const long long ntl = (long long)pt.tiles_w * pt.tiles_h * ((B + pt.bb - 1) / pt.bb);
+      pt.ntiles_m = (int)ntl;
+      pt.ksplit = 1;
+      pt.tma_store = 0;
+      if (pt.bb <= 256 && ntl < (1ll << 31)) {
+        CUtensorMap mapsT[B200_MAX_SRC];
+        memset(mapsT, 0, sizeof(mapsT));
+        for (int i = 0; i < nsrc; ++i) {
+          cuuint64_t dims[4] = {(cuuint64_t)srcs[i].C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+          cuuint64_t strides[3] = {(cuuint64_t)srcs[i].ld * 2, (cuuint64_t)srcs[i].ld * 2 * W, (cuuint64_t)srcs[i].ld * 2 * W * H};
+          cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)pt.bw, (cuuint32_t)pt.bh, (cuuint32_t)pt.bb};
+          cuuint32_t estr[4] = {1, 1, 1, 1};
+          CUresult r = enc(&mapsT[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(srcs[i].ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm(T): cuTensorMapEncodeTiled(X%d) failed with %d (box %d,%d,%d)", i, (int)r, pt.bw, pt.bh, pt.bb);
+        }
+        for (int i = nsrc; i < B200_MAX_SRC; ++i) mapsT[i] = mapsT[0];
+        CUtensorMap mapW;
+        {
+          cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Npad};
+          cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+          cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+          cuuint32_t estr[2] = {1, 1};
+          CUresult r = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm(T): cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+        }
+        constexpr int TS = 4;
+        constexpr int smemT = TS * T_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 2 * T_STG_BYTES;
+        static_assert(smemT <= 232448, "shared memory budget");
+        B200_SMEM_OPT_IN(conv_gemm_tcT_kernel<TS>, smemT);
+        const int grid = (int)(ntl < sm_count() ? ntl : sm_count());
+        B200_CUDA_OK(b200_launch(conv_gemm_tcT_kernel<TS>, dim3(grid), dim3(64 + 256), smemT, st, mapsT[0], mapsT[1], mapsT[2], mapsT[3], mapW, pt));
+        return B200_OK;
+      }
+    }
+  }
   // tile shape: CTA pairs (256 x BN per pair, B split across the pair) whenever there are >= 2 row tiles and >= 128 columns
   const bool pair = pair_enabled() && !has_norm && ntiles >= 2 && p.Npad >= 128;
   int BN;

@@ -192,12 +192,68 @@ def test_qk_l2norm_and_kv_scatter_epilogues(impl):
     assert Kb[:, :npre].abs().max() == 0                              # prefix rows untouched
 
 
-# ------------------------------------------------------------------------------------------------ norms fused into the GEMM epilogue
-
 def _ln_ref(x, g):
     mean, var = x.mean(-1, keepdim=True), x.var(-1, unbiased=False, keepdim=True)
     return (x - mean) * (var + 1e-5).rsqrt() * g
 
+
+# ------------------------------------------------------------------------------------------------ transposed kernel (<= 128 output channels, many rows)
+
+@pytest.mark.parametrize('case', ['conv3x3_plain', 'conv3x3_res', 'conv3x3_rms_film_only', 'conv3x3_raw_and_ln', 'two_sources_res_rms', 'ragged_96ch_silu', 'linear_k512'])
+def test_transposed_gemm_for_128_output_channels(case):
+    """conv_gemm_tcT_kernel: D^T = W X^T with the weights as the M = 128 operand and 256 pixels as the N operand, epilogue transposed through
+    shared memory; selected by b200_conv_gemm for Npad == 128, K >= 512 and >= one 256-pixel tile per SM.  Same torch fp32 references as the
+    row-major kernel's tests."""
+    cfg = {
+        'conv3x3_plain': dict(B=3, H=128, W=128, Cs=[128], N=128, k=3, res=False, n2=0, film=False, raw=True, act=0),
+        'conv3x3_res': dict(B=3, H=128, W=128, Cs=[128], N=128, k=3, res=True, n2=0, film=False, raw=True, act=0),
+        'conv3x3_rms_film_only': dict(B=10, H=64, W=64, Cs=[128], N=128, k=3, res=False, n2=2, film=True, raw=False, act=0),
+        'conv3x3_raw_and_ln': dict(B=10, H=64, W=64, Cs=[128], N=128, k=3, res=False, n2=1, film=False, raw=True, act=0),
+        'two_sources_res_rms': dict(B=10, H=64, W=64, Cs=[128, 64], N=128, k=3, res=True, n2=2, film=False, raw=True, act=0),
+        'ragged_96ch_silu': dict(B=5, H=100, W=130, Cs=[64], N=96, k=3, res=False, n2=2, film=True, raw=True, act=_lib.ACT_SILU),
+        'linear_k512': dict(B=1, H=1, W=40001, Cs=[512], N=128, k=1, res=True, n2=0, film=False, raw=True, act=0),
+    }[case]
+    B, H, W, Cs, N, k = (cfg[x] for x in ('B', 'H', 'W', 'Cs', 'N', 'k'))
+    M = B * H * W
+    assert M >= 256 * 148, 'too few rows to take the transposed kernel'
+    srcs = [rnd(B, H, W, c, seed=10 + i).to(BF16) for i, c in enumerate(Cs)]
+    Wt = rnd(N, sum(Cs), k, k, scale=1.0 / math.sqrt(sum(Cs) * k * k), seed=2)
+    bias = rnd(N, scale=0.1, seed=3)
+    res = (rnd(M, N, seed=4) * 1.5 + 0.3).to(BF16) if cfg['res'] else None
+    g2 = (1 + 0.2 * rnd(N, seed=6)).contiguous()
+    film = rnd(B, 2 * N + 8, scale=0.3, seed=7).contiguous() if cfg['film'] else None
+    out = torch.zeros(M, N, dtype=BF16, device=DEV) if cfg['raw'] else None
+    out_n = torch.zeros(M, N, dtype=BF16, device=DEV) if cfg['n2'] else None
+    segs, mats = ops.conv_segments(Wt, Cs)
+    call = ops.GemmCall([(x.data_ptr(), x.shape[-1], x.shape[-1]) for x in srcs], segs, (B, H, W), ops.pack_weight(mats, N, DEV), N,
+                        out.data_ptr() if out is not None else None, bias=ops.padded_bias(bias, N, DEV), act=cfg['act'],
+                        residual=res.data_ptr() if res is not None else None, ldr=N, ldc=N)
+    if cfg['n2']:
+        g2k = g2 * math.sqrt(N) if cfg['n2'] == 2 else g2
+        call.set_norm2(cfg['n2'], g2k.contiguous(), out_n.data_ptr(), N, film_ptr=film.data_ptr() if film is not None else None,
+                       film_ld=film.shape[1] if film is not None else 0, rows_per_sample=H * W)
+    call(stream())
+    torch.cuda.synchronize()
+    x = torch.cat([s_.float() for s_ in srcs], dim=-1)
+    v = F.conv2d(x.permute(0, 3, 1, 2), Wt.to(BF16).float(), bias, padding=k // 2).permute(0, 2, 3, 1).reshape(M, N)
+    if cfg['act'] == _lib.ACT_SILU:
+        v = F.silu(v)
+    w = v + (res.float() if res is not None else 0.)
+    if out is not None:
+        assert_close(out, w, 1.2e-2, 1.5e-2, f'{case}: raw')
+    if cfg['n2']:
+        if cfg['n2'] == 1:
+            y = _ln_ref(w, g2)
+        else:
+            y = F.normalize(w, dim=-1) * g2 * math.sqrt(N)
+            if film is not None:
+                fr = film.repeat_interleave(H * W, dim=0)
+                y = y * (fr[:, :N] + 1) + fr[:, N:2 * N]
+            y = F.silu(y)
+        assert_close(out_n, y, 1.2e-2, 1.5e-2, f'{case}: normalised')
+
+
+# ------------------------------------------------------------------------------------------------ norms fused into the GEMM epilogue
 
 @pytest.mark.parametrize('case', ['conv3x3_rms_film_only', 'linear_ln_res_ln', 'linear_ln_res_rms_film_only', 'linear_gelu_ln_only', 'conv_res_ln_lazy',
                                   'n64_rms', 'n192_ln_res_rms', 'n256_ln_res_ln', 'ragged_rows_rms'])

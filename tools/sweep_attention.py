@@ -7,7 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAMES = {0: 'nw4', 1: 'nw8', 2: 'nw8+pf', 3: 'nw16', 4: 'nw16+pf', 5: 'nw8+wa', 6: 'nw8+pf+wa', 7: 'nw16+pf+wa', 8: 'nw4+wa', 9: 'pingpong', 10: 'pp+poly1/4', 11: 'pp+poly1/2', 12: 'pp16', 13: 'pp16+poly1/4',
          20: 'pt16', 21: 'pt16+poly1/8', 23: 'pt16+poly1/4', 26: 'pt8', 27: 'pt8+poly1/4',
-         40: 'pt16 nosub', 41: 'pt16 nosub p1/8', 42: 'pt16 nosub p1/4', 43: 'pt16 nosub p1/3', 46: 'pt8 nosub', 47: 'pt8 nosub p1/4',
+         40: 'pt16 nosub', 41: 'pt16 nosub p1/8', 42: 'pt16 nosub p1/4', 43: 'pt16 nosub p1/3', 46: 'pt8 nosub', 47: 'pt8 nosub p1/4', 39: 'pt8 nosub p1/2', 48: 'pt8 nosub p1/3', 49: 'pt8 nosub p1/5', 44: 'pt8 nosub p1/6', 45: 'pt8 nosub p1/8',
          50: 'ABL no-MUFU', 51: 'ABL no-LDTM', 52: 'ABL neither',
          30: 'pt16+order', 31: 'pt16+order+p1/8', 32: 'pt16+order+p1/5', 33: 'pt16+order+p1/4', 34: 'pt16+order+p1/3', 36: 'pt8+order', 37: 'pt8+order+p1/4'}
 CODE = '''
@@ -34,12 +34,15 @@ for nk in (256 + 39 + 128, 256 + 100, 384, 512 + 64, 257):
 print('RESULT %%.4f ms  %%.1f TFLOP/s  maxdiff %%.4f' %% (ms, 1109.98 / ms, md))
 ''' % ROOT
 
-only = [int(v) for v in os.environ.get('SWEEP_VARIANTS', '').split(',') if v.strip()]
-for var in (only or sorted(NAMES)):
-    env = dict(os.environ, B200_IMAGEN_FA_VARIANT=str(var))
+# SWEEP_VARIANTS="20,47,47:500": variant[:barrier-wait suspend hint in ns]
+only = [v.strip() for v in os.environ.get('SWEEP_VARIANTS', '').split(',') if v.strip()]
+for spec in (only or [str(v) for v in sorted(NAMES)]):
+    var, _, ns = spec.partition(':')
+    var = int(var)
+    env = dict(os.environ, B200_IMAGEN_FA_VARIANT=str(var), B200_IMAGEN_FA_WAIT_NS=ns or '0')
     try:
         out = subprocess.run([sys.executable, '-c', CODE], env=env, capture_output=True, text=True, timeout=300)
         res = [l for l in out.stdout.splitlines() if l.startswith('RESULT')]
-        print(f'variant {var} {NAMES.get(var, "?"):12s}', res[0] if res else ('FAILED ' + out.stderr[-300:]))
+        print(f'variant {spec:8s} {NAMES.get(var, "?"):16s}', res[0] if res else ('FAILED ' + out.stderr[-300:]))
     except subprocess.TimeoutExpired:
         print(f'variant {var} {NAMES[var]:12s} TIMEOUT')
