@@ -379,14 +379,14 @@ def main():
         # MUFU floor of head-dim-64 attention: one exp2 per score, 16 exp2/clk/SM measured (profiles/r01_mufu_ex2_microbench.txt)
         n_exp = R * 8 * 4096 * ((4096 + 39 + 127) // 128 * 128)
         mufu_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
-        line['roofline'] = {'kernel': 'flash_attn_pp_kernel (tcgen05 multi-query self-attention, 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
+        line['roofline'] = {'kernel': 'flash_attn_pt_kernel<0,2,0,1> (tcgen05 multi-query self-attention, P in tensor memory; 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
                             'bound': 'tensor', 'achieved': att_tflops, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': att_tflops / pk['tensor_burst'],
-                            'traffic': 262.4e6, 'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_flash_attn_pp_summary.txt); algorithmic q+o+k+v = 285 MB',
+                            'traffic': 262.1e6, 'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r02_ncu_flash_attn_pt_summary.txt); algorithmic q+o+k+v = 285 MB',
                             'ms_per_launch': att_ms, 'algorithmic_gflop_per_launch': ATTN_L0_GFLOP_PER_SAMPLE * R,
                             'peak_source': f"{pk['src']} burst bf16 (kernel timed alone)",
                             'mufu_floor_ms': mufu_ms, 'frac_of_mufu_floor': mufu_ms / att_ms}
         conv_ms, conv_gflop = time_conv_kernel(R, device)
-        line['roofline_conv'] = {'kernel': 'conv_gemm_tc_kernel<128,6,STAGED,8> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64)', 'bound': 'tensor',
+        line['roofline_conv'] = {'kernel': 'conv_gemm_tcT_kernel<4> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64, transposed: weights = M operand, 256 pixels = N operand)', 'bound': 'tensor',
                                  'achieved': conv_gflop / conv_ms, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': conv_gflop / conv_ms / pk['tensor_burst'],
                                  'traffic': 34.0e6, 'ms_per_launch': conv_ms, 'algorithmic_gflop_per_launch': conv_gflop,
                                  'note': 'L2 flushed between launches; dram traffic from ncu = 33.9 MB read (input 33.5 MB read once), output stays in L2'}

@@ -71,6 +71,7 @@ SIGNATURES = {
     'b200_layernorm': [_P, _I, _P, _P, _F, _P, _I, _P, _I, _L, _I, _P],
     'b200_gca_gate': [_P, _I, _I, _I, _I, _P, _F, _P, _P, _I, _P, _P, _P, _I, _P, _P],
     'b200_gca_nchunk': [_I],
+    'b200_gca_chunks': [_I, _I],
     'b200_gate_residual': [_P, _I, _P, _P, _I, _P, _I, _L, _I, _I, _P],
     'b200_im2col_init': [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     'b200_im2col_init3': [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],

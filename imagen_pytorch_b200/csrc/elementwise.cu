@@ -1,7 +1,8 @@
 // HBM-bound row-wise kernels on NHWC bf16 pixel rows: ChanRMSNorm+FiLM+SiLU, LayerNorm(+residual),
 // GlobalContext gate, gate*x+residual, layout gathers, per-step time-conditioning plumbing.
 // Reference arithmetic replaced: see include/b200_imagen.h next to each entry point.
-#include "common.cuh"
+#include "ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -288,6 +289,196 @@ __global__ void __launch_bounds__(GCA_THREADS) gca_pool_kernel(const __nv_bfloat
   }
 }
 
+// logits + pooling fused: the pixel chunk is staged ONCE in shared memory (the separate logits kernel read the whole tensor a second time):
+//   x chunk -> smem;  logit[p] = x[p, :] . wk + bk (warp per pixel);  chunk max / exp weights / sum;  weighted channel sums -> partial
+__global__ void __launch_bounds__(GCA_THREADS) gca_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows_per_sample, int C,
+                                                                     const float* __restrict__ wk, float bk, int nchunk, float* __restrict__ scratch) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ uint8_t gca_smem[];
+  __shared__ float red[GCA_THREADS * 8];
+  __shared__ float sred[16];
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
+  const int p0 = chunk * ppc, np = max(0, min(rows_per_sample, p0 + ppc) - p0);
+  const int vecs = C >> 3;
+  uint4* xs = reinterpret_cast<uint4*>(gca_smem);                               // [ppc][vecs]
+  float* sw = reinterpret_cast<float*>(gca_smem + (size_t)ppc * C * 2);         // [ppc] logits, then weights
+  float* out = scratch + ((long long)b * nchunk + chunk) * (C + 2);
+  const __nv_bfloat16* xb = x + ((long long)b * rows_per_sample + p0) * ldx;
+  for (int i = tid; i < np * vecs; i += GCA_THREADS) {
+    const int p = i / vecs, v = i - p * vecs;
+    xs[i] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)p * ldx + (v << 3)));
+  }
+  __syncthreads();
+  for (int p = warp; p < np; p += GCA_THREADS / 32) {                           // logits: one warp per pixel
+    float dot = 0.f;
+    for (int v = lane; v < vecs; v += 32) {
+      float f[8];
+      unpack8(xs[p * vecs + v], f);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wk + (v << 3)));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wk + (v << 3) + 4));
+      dot += f[0] * w0.x + f[1] * w0.y + f[2] * w0.z + f[3] * w0.w + f[4] * w1.x + f[5] * w1.y + f[6] * w1.z + f[7] * w1.w;
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) sw[p] = dot + bk;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int p = tid; p < np; p += GCA_THREADS) m = fmaxf(m, sw[p]);
+  m = warp_max(m);
+  if (lane == 0) sred[warp] = m;
+  __syncthreads();
+  m = sred[0];
+#pragma unroll
+  for (int w = 1; w < GCA_THREADS / 32; ++w) m = fmaxf(m, sred[w]);
+  float l = 0.f;
+  for (int p = tid; p < np; p += GCA_THREADS) {
+    const float e = __expf(sw[p] - m);
+    sw[p] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  if (lane == 0) sred[8 + warp] = l;
+  __syncthreads();
+  const int npl = GCA_THREADS / vecs > 0 ? GCA_THREADS / vecs : 1;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (vecs <= GCA_THREADS) {
+    const int cv = tid % vecs, pl = tid / vecs;
+    if (pl < npl) {
+#pragma unroll 4
+      for (int p = pl; p < np; p += npl) {
+        float f[8];
+        unpack8(xs[p * vecs + cv], f);
+        const float w = sw[p];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += w * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[tid * 8 + j] = acc[j];
+    __syncthreads();
+    for (int c = tid; c < C; c += GCA_THREADS) {
+      const int v = c >> 3, j = c & 7;
+      float s = 0.f;
+      for (int q = 0; q < npl; ++q) s += red[(q * vecs + v) * 8 + j];
+      out[2 + c] = s;
+    }
+  } else {                                                                      // C > 2048: every thread walks several channel vectors
+    for (int cv = tid; cv < vecs; cv += GCA_THREADS) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < np; ++p) {
+        float f[8];
+        unpack8(xs[p * vecs + cv], f);
+        const float w = sw[p];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += w * f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[2 + (cv << 3) + j] = a[j];
+    }
+  }
+  if (tid == 0) {
+    float L = 0.f;
+#pragma unroll
+    for (int w = 0; w < GCA_THREADS / 32; ++w) L += sred[8 + w];
+    out[0] = np > 0 ? m : -INFINITY;
+    out[1] = L;
+  }
+}
+
+// combine + both layers of the gate MLP in ONE launch: a cluster of 8 CTAs serves up to 8 samples.  Every CTA rebuilds the pooled vectors of
+// its samples from the chunk partials (tiny), computes its 1/8 slice of the hidden layer for all samples at once (each weight row is
+// streamed once per cluster), publishes it in shared memory, and after one cluster barrier reads the other seven slices through
+// distributed shared memory to compute its 1/8 slice of the sigmoid gate.  Replaces gca_combine + 2 x gca_mlp (3 launches of ~8 us each).
+constexpr int GCA_CL = 8;
+constexpr int GCA_TB = 8;    // samples per cluster
+__global__ void __cluster_dims__(GCA_CL, 1, 1) __launch_bounds__(256)
+gca_tail_kernel(const float* __restrict__ scratch, int nchunk, int C, int hidden, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gate, int B) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float tail_smem[];
+  const int hs = (hidden + GCA_CL - 1) / GCA_CL, cs = (C + GCA_CL - 1) / GCA_CL;
+  float* pooled = tail_smem;                       // [GCA_TB][C]
+  float* hid_all = pooled + GCA_TB * C;            // [GCA_TB][hs * GCA_CL]
+  float* hid_loc = hid_all + GCA_TB * hs * GCA_CL; // [GCA_TB][hs]   (read by the peers)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = blockIdx.y * GCA_TB;
+  const int nb = B - b0 < GCA_TB ? B - b0 : GCA_TB;
+  // ---- combine the online-softmax partials of every sample of this cluster (redundantly in each CTA)
+  for (int i = tid; i < nb * C; i += 256) {
+    const int b = i / C, c = i - b * C;
+    const float* sc = scratch + (long long)(b0 + b) * nchunk * (C + 2);
+    float M = -INFINITY;
+    for (int k = 0; k < nchunk; ++k) M = fmaxf(M, sc[(long long)k * (C + 2)]);
+    float L = 0.f, a = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+      const float mk = sc[(long long)k * (C + 2)];
+      if (mk == -INFINITY) continue;
+      const float e = __expf(mk - M);
+      L += sc[(long long)k * (C + 2) + 1] * e;
+      a += sc[(long long)k * (C + 2) + 2 + c] * e;
+    }
+    pooled[b * C + c] = a / L;
+  }
+  __syncthreads();
+  // ---- hidden slice: one warp per output row, all samples at once
+  for (int n = (int)rank * hs + warp; n < (int)(rank + 1) * hs && n < hidden; n += 8) {
+    float acc[GCA_TB];
+#pragma unroll
+    for (int b = 0; b < GCA_TB; ++b) acc[b] = 0.f;
+    const float* wr = w1 + (long long)n * C;
+    for (int k = lane * 4; k < C; k += 128) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int b = 0; b < GCA_TB; ++b)
+        if (b < nb) {
+          const float4 xv = *reinterpret_cast<const float4*>(pooled + b * C + k);
+          acc[b] += w.x * xv.x + w.y * xv.y + w.z * xv.z + w.w * xv.w;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < GCA_TB; ++b) {
+      const float s = warp_sum(acc[b]);
+      if (lane == 0 && b < nb) hid_loc[b * hs + (n - (int)rank * hs)] = silu_f(s + b1[n]);
+    }
+  }
+  cluster_sync_all();
+  // ---- gather the eight hidden slices through distributed shared memory
+  for (int i = tid; i < GCA_CL * nb * hs; i += 256) {
+    const int rr = i / (nb * hs), rem = i - rr * (nb * hs);
+    const int b = rem / hs, j = rem - b * hs;
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_u32(smem_u32(hid_loc + b * hs + j), (uint32_t)rr)) : "memory");
+    hid_all[b * (hs * GCA_CL) + rr * hs + j] = v;
+  }
+  __syncthreads();
+  // ---- gate slice
+  for (int c = (int)rank * cs + warp; c < (int)(rank + 1) * cs && c < C; c += 8) {
+    float acc[GCA_TB];
+#pragma unroll
+    for (int b = 0; b < GCA_TB; ++b) acc[b] = 0.f;
+    const float* wr = w2 + (long long)c * hidden;
+    for (int k = lane * 4; k < hidden; k += 128) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int b = 0; b < GCA_TB; ++b)
+        if (b < nb) {
+          const float* xv = hid_all + b * (hs * GCA_CL) + k;
+          acc[b] += w.x * xv[0] + w.y * xv[1] + w.z * xv[2] + w.w * xv[3];
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < GCA_TB; ++b) {
+      const float s = warp_sum(acc[b]);
+      if (lane == 0 && b < nb) gate[(long long)(b0 + b) * C + c] = sigmoid_f(s + b2[c]);
+    }
+  }
+  cluster_sync_all();          // no CTA leaves while a peer may still read its hidden slice
+}
+
 // combine the per-chunk online-softmax partials -> pooled[b, c]
 __global__ void __launch_bounds__(256) gca_combine_kernel(const float* __restrict__ scratch, int nchunk, int C, float* __restrict__ pooled) {
   pdl_trigger();
@@ -545,6 +736,13 @@ extern "C" int b200_gca_nchunk(int32_t rows_per_sample) {
   return n;
 }
 
+extern "C" int b200_gca_chunks(int32_t rows_per_sample, int32_t C) {
+  int ppc = 256;
+  while (ppc > 8 && (long long)ppc * C * 2 > 128 * 1024) ppc >>= 1;   // the fused pooling kernel stages its pixel chunk in shared memory
+  int n = (rows_per_sample + ppc - 1) / ppc;
+  return n < 1 ? 1 : n;
+}
+
 extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C, const float* wk, float bk,
                              const float* w1, const float* b1, int32_t hidden, const float* w2, const float* b2, float* scratch,
                              int32_t nchunk, float* gate, void* stream) {
@@ -561,10 +759,24 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
   float* partials = hid + (long long)B * hidden;
   float* logits = partials + (long long)B * nchunk * (C + 2);
   const long long M = (long long)B * rows_per_sample;
+  static const bool fused_on = [] { const char* ev = getenv("B200_IMAGEN_GCA_FUSED"); return ev == nullptr || atoi(ev) != 0; }();
+  const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
+  const size_t pool_smem = (size_t)ppc * C * 2 + (size_t)ppc * 4;
+  const int hs = (hidden + GCA_CL - 1) / GCA_CL;
+  const size_t tail_smem = ((size_t)GCA_TB * C + (size_t)GCA_TB * hs * GCA_CL + (size_t)GCA_TB * hs) * 4;
+  if (fused_on && pool_smem <= 160 * 1024 && tail_smem <= 160 * 1024 && (C & 3) == 0) {
+    // 2 launches: fused logits + pooling (pixel chunk staged once in shared memory), then the cluster kernel combine -> MLP -> gate
+    B200_SMEM_OPT_IN(gca_pool_fused_kernel, 200 * 1024);
+    B200_CUDA_OK(b200_launch(gca_pool_fused_kernel, dim3(nchunk, B), dim3(GCA_THREADS), pool_smem, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                             rows_per_sample, C, wk, bk, nchunk, partials));
+    B200_SMEM_OPT_IN(gca_tail_kernel, 200 * 1024);
+    gca_tail_kernel<<<dim3(GCA_CL, (B + GCA_TB - 1) / GCA_TB), 256, tail_smem, st>>>(partials, nchunk, C, hidden, w1, b1, w2, b2, gate, B);
+    B200_LAUNCH_OK();
+    return B200_OK;
+  }
   const int vecs = C >> 3;
   const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
   DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
-  B200_LAUNCH_OK();
   B200_CUDA_OK(b200_launch(gca_pool_kernel, dim3(nchunk, B), dim3(GCA_THREADS), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials));
   B200_CUDA_OK(b200_launch(gca_combine_kernel, dim3((C + 255) / 256, B), dim3(256), 0, st, partials, nchunk, C, pooled));
   const int bg = (B + 7) / 8;

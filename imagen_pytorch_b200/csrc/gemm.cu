@@ -52,6 +52,7 @@ struct GemmParams {
   int nseg, total_chunks, ntiles_m;
   int ksplit;      // > 1: K is split over ksplit adjacent work items; each writes its raw fp32 partial tile to out + split * M * ldc
   int tma_store;   // staged epilogue hands each 32-row x 32-column group to a TMA store (plain bf16 row-major destinations)
+  uint32_t wait_ns;   // suspend-time hint of the producer / issuer barrier waits (0 = plain spin); B200_IMAGEN_GEMM_WAIT_NS
   int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads, 8 no wait before restaging (WRONG results), 16 no proxy fence (WRONG results)
   int nchunks[B200_MAX_SRC];
   SegDev seg[B200_MAX_SEG];
@@ -789,7 +790,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
             if (kc < kc0 || kc >= kc1) continue;   // another split's share of K
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
             if (p.debug & 4) {
               mbar_arrive(&full_bar[stage]);
             } else {
@@ -811,13 +812,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator stage
+        mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1u, p.wait_ns);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         const int split = t % ksplit;
         const int nkc = (split + 1) * p.total_chunks / ksplit - split * p.total_chunks / ksplit;
         for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
@@ -855,7 +856,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int tile = (int)((unsigned)tt / (unsigned)n_tiles_n), n0 = (tt - tile * n_tiles_n) * BN;
       RowInfo ri = tile_row(p, tile, rit);
       if (p.ksplit > 1) ri.orow += (long long)split * p.B * p.H * p.W;   // partial tiles: [split][row][col] fp32
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait_sleep(&tmem_full_bar[acc], acc_phase, p.wait_ns);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
       if (!(p.debug & 1)) {
@@ -1060,6 +1061,157 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------ tcgen05 kernel, K split across a cluster
+// The coarsest U-Net levels (8 x 8 pixels x 32 rows = 2048 output rows, 1024 channels, K = 9216 .. 13824) give only 64 tiles of 128 x 256 on
+// 148 SMs; with 128 x 128 tiles (128 CTAs) they run at the N = 128 instruction rate (~700 TFLOP/s).  Splitting K through a global-memory
+// workspace lost to the extra launch and the 16 MB partial round trip (profiles/r01_gemm_splitk_ab.txt).  Here the K range of ONE 128 x 256
+// output tile is split across the 2..4 CTAs of a thread-block cluster: every CTA runs the usual TMA -> tcgen05 pipeline over its share of
+// the K chunks, the non-zero ranks park their fp32 accumulator in their own shared memory (over the drained operand ring), and after one
+// cluster barrier rank 0 adds the partial tiles through distributed shared memory inside its normal epilogue.  One launch, no HBM traffic,
+// partials are added in rank order (deterministic).
+constexpr int KS_BN = 256;
+constexpr int KS_STAGES = 4;
+constexpr int KS_STAGE_BYTES = A_TILE_BYTES + KS_BN * BK * 2;
+constexpr int KS_PITCH = KS_BN + 4;                      // floats per parked accumulator row (bank-conflict-free float4 rows)
+
+__global__ void __launch_bounds__(64 + 256, 1)
+conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+                     const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+                     const __grid_constant__ GemmParams p) {
+  pdl_trigger();
+  constexpr int HALVES = 2, BNH = KS_BN / HALVES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + KS_STAGES * KS_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + KS_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + KS_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* parked = reinterpret_cast<float*>(smem);        // [128][KS_PITCH] fp32, overlays the operand ring once the MMAs have completed
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int nsplit = p.ksplit;
+  const int n_tiles_n = p.Npad / KS_BN;
+  const int tt = (int)blockIdx.x / nsplit;
+  const int tile = tt / n_tiles_n, n0 = (tt % n_tiles_n) * KS_BN;
+  const int kc0 = (int)rank * p.total_chunks / nsplit, kc1 = ((int)rank + 1) * p.total_chunks / nsplit;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.nchunks[1] > 0) tma_prefetch_desc(&mapA1);
+    if (p.nchunks[2] > 0) tma_prefetch_desc(&mapA2);
+    if (p.nchunks[3] > 0) tma_prefetch_desc(&mapA3);
+    tma_prefetch_desc(&mapB);
+    if (p.tma_store) tma_prefetch_desc(&mapO);
+    for (int s = 0; s < KS_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)KS_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: this rank's share of the K chunks
+      const int wblk = tile % p.tiles_w;
+      const int hblk = (tile / p.tiles_w) % p.tiles_h;
+      const int bblk = tile / (p.tiles_w * p.tiles_h);
+      const int w0 = wblk * p.bw, h0 = hblk * p.bh, b0 = bblk * p.bb;
+      int stage = 0, kc = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int src = p.seg[s].src;
+        const CUtensorMap* mA = src == 0 ? &mapA0 : (src == 1 ? &mapA1 : (src == 2 ? &mapA2 : &mapA3));
+        const int dh = p.seg[s].dh, dw = p.seg[s].dw;
+        const int nch = p.nchunks[src];
+        for (int cc = 0; cc < nch; ++cc, ++kc) {
+          if (kc < kc0 || kc >= kc1) continue;
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
+          mbar_expect_tx(&full_bar[stage], KS_STAGE_BYTES);
+          uint8_t* sA = smem + stage * KS_STAGE_BYTES;
+          tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
+          tma_load_2d(sA + A_TILE_BYTES, &mapB, &full_bar[stage], kc * BK, n0);
+          if (++stage == KS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KS_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < kc1 - kc0; ++kc) {
+        mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * KS_STAGE_BYTES);
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == KS_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (rank != 0) {
+    // ---------------- non-zero ranks: accumulator -> own shared memory (row = thread, KS_PITCH floats per row)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    mbar_wait_sleep(tmem_full_bar, 0, p.wait_ns);          // every MMA of this CTA has completed: the operand ring is free
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BNH);
+    float* row = parked + (size_t)(q * 32 + lane) * KS_PITCH + half * BNH;
+#pragma unroll 1
+    for (int c = 0; c < BNH; c += 32) {
+      float v[32];
+      tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v));
+      tmem_wait_regs32(v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();                                     // #1: the partial tiles are parked and visible cluster-wide
+  if (warp >= 2 && rank == 0) {
+    // ---------------- rank 0: the normal staged epilogue over (own accumulator + parked partials of ranks 1..nsplit-1, in rank order)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const RowInfo ri = tile_row(p, tile, row_in_tile(p, q * 32 + lane));
+    mbar_wait_sleep(tmem_full_bar, 0, p.wait_ns);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BNH);
+    const uint32_t my_row = smem_u32(parked + (size_t)(q * 32 + lane) * KS_PITCH + half * BNH);
+    const uint32_t stg = smem_u32(smem + KS_STAGES * KS_STAGE_BYTES + 1024 + (warp - 2) * EPI_STAGE_BYTES);
+    int cur_c = 0;
+    epilogue_staged<BNH, false>(p, &mapO, ri, n0 + half * BNH, stg, stg + 2048u, lane,
+                                [&](int c, float* v) { cur_c = c; tmem_ld32_nowait(taddr + (uint32_t)c, reinterpret_cast<uint32_t*>(v)); },
+                                [&](float* v) {
+                                  tmem_wait_regs32(v);
+                                  for (int rr = 1; rr < nsplit; ++rr) {
+                                    const uint32_t ra = mapa_u32(my_row + (uint32_t)cur_c * 4u, (uint32_t)rr);
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 4) {
+                                      float4 t;
+                                      asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(ra + (uint32_t)j * 4u) : "memory");
+                                      v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                                    }
+                                  }
+                                });
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+  }
+  cluster_sync_all();                                     // #2: rank 0 has read every partial tile; nobody exits before that
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)KS_BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ tcgen05 kernel, transposed (<= 128 output channels)
 // For layers with <= 128 output channels the M128 x N128 MMA of the kernel above is the bottleneck: every K=16 instruction reads 4 KB of A
 // and 4 KB of B from shared memory for 64 cycles of math and the two do not overlap (878 TFLOP/s issue-only, vs 1398 for N = 256;
@@ -1137,7 +1289,7 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           const int dh = p.seg[s].dh, dw = p.seg[s].dw;
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
             mbar_expect_tx(&full_bar[stage], T_STAGE_BYTES);
             uint8_t* sW = smem + stage * T_STAGE_BYTES;
             tma_load_2d(sW, &mapW, &full_bar[stage], kc * BK, 0);
@@ -1154,11 +1306,11 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1u, p.wait_ns);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T_BP);
         for (int kc = 0; kc < p.total_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
           tc_fence_after();
           const uint32_t w_addr = smem_u32(smem + stage * T_STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(w_addr);
@@ -1189,7 +1341,7 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait_sleep(&tmem_full_bar[acc], acc_phase, p.wait_ns);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T_BP + grp * 128);
 #pragma unroll 1
@@ -1514,6 +1666,8 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   {
     static const int dbg = [] { const char* e = getenv("B200_IMAGEN_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
+    static const uint32_t wns = [] { const char* e = getenv("B200_IMAGEN_GEMM_WAIT_NS"); return (uint32_t)(e ? atoi(e) : 0); }();
+    p.wait_ns = wns;
   }
   for (int i = 0; i < nsrc; ++i) {
     B200_REQUIRE(srcs[i].ptr != nullptr && srcs[i].C > 0, "conv_gemm: src %d empty", i);
@@ -1614,7 +1768,10 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
                        (N & 15) == 0 && (e.out == nullptr || ((e.ldc & 7) == 0 && al16(e.out))) && (e.out != nullptr || e.norm2 != 0) &&
                        (e.residual == nullptr || ((e.ldr & 7) == 0 && al16(e.residual))) && (e.norm2 == 0 || (al16(e.out_norm) && (e.ld_norm & 7) == 0)) &&
                        Mll < (1ll << 31);
-    if (t_on && p.Npad == 128 && t_epi && total >= 8 && Mll >= (long long)T_BP * sm_count()) {   // at least one 256-pixel tile per SM
+    // measured on B200 (profiles/r02_gemm_transposed_ab.txt): plain 3x3 conv 128->128 @64x64 54.8 -> 47.6 us; the HBM-bound K = 512 linears and the
+    // norm-fused K = 1152 convs are slower on it (its 8-warp transposing epilogue is not hidden behind 18 K chunks) -> long-K or norm-free only
+    const bool t_shape = total >= 16 && (e.norm2 == 0 || total >= 32);
+    if (t_on && p.Npad == 128 && t_epi && t_shape && Mll >= (long long)T_BP * sm_count()) {   // at least one 256-pixel tile per SM
       GemmParams pt = p;
       pt.bw = W >= T_BP ? T_BP : next_pow2(W);
       pt.bh = next_pow2(H) < T_BP / pt.bw ? next_pow2(H) : T_BP / pt.bw;
@@ -1724,6 +1881,45 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm: cuTensorMapEncodeTiled(out) failed with %d (N=%d ldc=%d W=%d H=%d B=%d)", (int)r, N, e.ldc, W, H, B);
       p.tma_store = 1;
+    }
+  }
+  // ---- K split across a thread-block cluster for few-tile, long-K GEMMs (conv_gemm_tcS_kernel)
+  {
+    static const bool ks_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_CLUSTER_K"); return ev == nullptr || atoi(ev) != 0; }();
+    const long long t256 = (long long)ntiles * (p.Npad / 256);
+    if (ks_on && !pair && !has_norm && ks <= 1 && p.Npad % 256 == 0 && gemm_is_simple(p) && e.l2_cols == 0 && t256 * 2 <= sm_count()) {
+      int split = (int)(sm_count() / t256);
+      if (split > 4) split = 4;
+      while (split > 1 && total / split < 16) --split;
+      if (split >= 2) {
+        // the B map of this path always has a 256-row box
+        CUtensorMap mapB2;
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Npad};
+        cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)KS_BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&mapB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_packed), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        B200_REQUIRE(r == CUDA_SUCCESS, "conv_gemm(K-split): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+        GemmParams pk = p;
+        pk.ksplit = split;
+        constexpr int smemS = KS_STAGES * KS_STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + 8 * EPI_STAGE_BYTES;
+        static_assert(smemS <= 232448 && 128 * KS_PITCH * 4 <= KS_STAGES * KS_STAGE_BYTES, "shared memory budget");
+        B200_SMEM_OPT_IN(conv_gemm_tcS_kernel, smemS);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(t256 * split));
+        cfg.blockDim = dim3(64 + 256);
+        cfg.dynamicSmemBytes = smemS;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)split; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_gemm_tcS_kernel, maps[0], maps[1], maps[2], maps[3], mapB2, mapO, pk));
+        return B200_OK;
+      }
     }
   }
   if (ks > 1) {

@@ -342,7 +342,7 @@ class UnetPlan:
         sd, R = self.sdc, self.R
         n, Cc = h.H * h.W, h.C
         hid = sd[p + '.net.0.weight'].shape[0]
-        nchunk = self.lib.b200_gca_nchunk(n)
+        nchunk = self.lib.b200_gca_chunks(n, Cc)
         scratch = self._zeros((R * nchunk * (Cc + 2) + R * Cc + R * hid + R * n,), torch.float32)
         gate = self._zeros((R, Cc), torch.float32)
         wk = self._f32(sd[p + '.to_k.weight'].flatten())
@@ -583,8 +583,8 @@ class UnetPlan:
             dst.copy_(src.expand_as(dst))
         self._post = None
         del self.sdc
-        # our kernel launches per U-Net evaluation (b200_gca_gate = logits + pool + combine + 2 MLP kernels)
-        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 4 + \
+        # our kernel launches per U-Net evaluation (b200_gca_gate = fused logits/pooling kernel + cluster MLP kernel)
+        self.n_launches = len(self._ops) + sum(1 for o in self._ops if o[2] == 'b200_gca_gate') * 1 + \
             sum(1 for c in self._keep if getattr(c, 'desc', {}).get('ksplit', 1) > 1)      # + split-K finishing kernels (GemmCall.desc)
 
     # ------------------------------------------------------------------ execution

@@ -184,6 +184,9 @@ int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, in
                   const float* wk, float bk, const float* w1, const float* b1, int32_t hidden,
                   const float* w2, const float* b2, float* scratch, int32_t nchunk, float* gate, void* stream);
 int b200_gca_nchunk(int32_t rows_per_sample);
+/* chunk count for which b200_gca_gate takes its 2-launch path (fused logits + pooling with the pixel chunk staged in shared memory, then
+ * one cluster kernel for combine + MLP + gate); the scratch layout is the same with this nchunk */
+int b200_gca_chunks(int32_t rows_per_sample, int32_t C);
 
 /* out = x * gate[b, c] + residual  (ResnetBlock.forward imagen_pytorch.py:755-757). */
 int b200_gate_residual(const void* x, int32_t ldx, const float* gate, const void* residual, int32_t ldr,

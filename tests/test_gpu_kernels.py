@@ -95,7 +95,9 @@ CONV_CASES = {
     'c3_24x24_nonpow2_32to32': dict(B=2, H=24, W=24, Cs=[32], N=32, k=3),
     'c1_16x16_192to512': dict(B=2, H=16, W=16, Cs=[192], N=512, k=1),
     'c3_128wide_64to64': dict(B=1, H=4, W=256, Cs=[64], N=64, k=3),
-    'c3_8x8_1536to1024_deepK': dict(B=4, H=8, W=8, Cs=[1024, 512], N=1024, k=3),
+    'c3_8x8_1536to1024_deepK': dict(B=4, H=8, W=8, Cs=[1024, 512], N=1024, k=3),          # 8 tiles of 128 x 256: K split over a 4-CTA cluster
+    'c3_8x8_256to1024_b32_cluster_k2': dict(B=32, H=8, W=8, Cs=[256], N=1024, k=3),       # 64 tiles: K split over CTA pairs
+    'c3_8x8_512to768_b26_cluster_k3': dict(B=26, H=8, W=8, Cs=[512], N=768, k=3),         # 13 x 3 tiles: 3-CTA clusters
 }
 
 
@@ -439,15 +441,14 @@ def test_layernorm_many_rows(Cc, residual, pitch):
     assert_close(out, ref, rtol=8e-3, atol=4e-3)
 
 
-@pytest.mark.parametrize('n,Cc', [(4096, 128), (64, 1024), (300, 40)])
-def test_global_context_gate_and_gate_residual(n, Cc):
-    B = 3
+@pytest.mark.parametrize('n,Cc,B', [(4096, 128, 3), (64, 1024, 3), (300, 40, 3), (256, 512, 11), (1024, 256, 32), (16, 2048, 9)])
+def test_global_context_gate_and_gate_residual(n, Cc, B):
     hid = max(3, Cc // 2)
     x = rnd(B * n, Cc).to(BF16)
     wk, bk = rnd(Cc, scale=0.2, seed=1), 0.1
     w1, b1 = rnd(hid, Cc, scale=1 / math.sqrt(Cc), seed=2), rnd(hid, scale=0.1, seed=3)
     w2, b2 = rnd(Cc, hid, scale=1 / math.sqrt(hid), seed=4), rnd(Cc, scale=0.1, seed=5)
-    nchunk = _lib.load().b200_gca_nchunk(n)
+    nchunk = _lib.load().b200_gca_chunks(n, Cc)
     scratch = torch.zeros(B * nchunk * (Cc + 2) + B * Cc + B * hid + B * n, device=DEV)
     gate = torch.zeros(B, Cc, device=DEV)
     _lib.call('b200_gca_gate', x.data_ptr(), Cc, B, n, Cc, wk.data_ptr(), bk, w1.data_ptr(), b1.data_ptr(), hid, w2.data_ptr(), b2.data_ptr(),
