@@ -56,6 +56,14 @@ class EdmCoef(C.Structure):
                                           'has_second', 'pad0', 'pad1', 'pad2')]
 
 
+class RowChain(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('ldx', C.c_int32), ('gate', C.c_void_p), ('rows_per_sample', C.c_int32),
+                ('norm1', C.c_int32), ('norm1_g', C.c_void_p), ('residual', C.c_void_p), ('ldr', C.c_int32),
+                ('out', C.c_void_p), ('ldo', C.c_int32), ('norm2', C.c_int32), ('norm2_g', C.c_void_p),
+                ('film', C.c_void_p), ('film_ld', C.c_int32), ('out_norm', C.c_void_p), ('ld_norm', C.c_int32),
+                ('M', C.c_int64), ('C', C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes: mirrors include/b200_imagen.h one to one (tests/test_abi.py checks every symbol)
@@ -70,6 +78,7 @@ SIGNATURES = {
     'b200_rmsnorm_film_silu': [C.POINTER(Src), _I, _F, _P, _P, _I, _I, _P, _I, _L, _P],
     'b200_layernorm': [_P, _I, _P, _P, _F, _P, _I, _P, _I, _L, _I, _P],
     'b200_gca_gate': [_P, _I, _I, _I, _I, _P, _F, _P, _P, _I, _P, _P, _P, _I, _P, _P],
+    'b200_row_chain': [C.POINTER(RowChain), _P],
     'b200_gca_nchunk': [_I],
     'b200_gca_chunks': [_I, _I],
     'b200_gate_residual': [_P, _I, _P, _P, _I, _P, _I, _L, _I, _I, _P],

@@ -31,6 +31,7 @@ extern "C" int b200_sizeof(int which) {
     case 3: return (int)sizeof(b200_timerow_job);
     case 4: return (int)sizeof(b200_ddpm_coef);
     case 5: return (int)sizeof(b200_edm_coef);
+    case 6: return (int)sizeof(b200_rowchain);
     default: return -1;
   }
 }

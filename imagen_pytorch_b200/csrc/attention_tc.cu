@@ -28,8 +28,8 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_DEFAULT_VARIANT = 40;   // ping-pong, P in tensor memory, 16 softmax warps, P = exp2(S) (profiles/r02_attention_variant_sweep.txt)
-constexpr int FA_DEFAULT_WAIT_NS = 200;  // barrier waits park instead of spinning (1.58 -> 1.47 ms, profiles/r02_attention_wait_hint_sweep.txt)
+constexpr int FA_DEFAULT_VARIANT = 41;   // ping-pong, P in tensor memory, 16 softmax warps, P = exp2(S), 1/8 of the exp2 on the FMA pipe
+constexpr int FA_DEFAULT_WAIT_NS = 100;  // barrier waits park instead of spinning (1.58 -> 1.41 ms, profiles/r02_attention_wait_hint_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
@@ -900,6 +900,8 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 30: PT_LAUNCH(0, 2, true, 0); break;    // + MUFU token between the two groups (slower: profiles/r02_attention_variant_sweep.txt)
     case 40: PT_LAUNCH(0, 2, false, 1); break;   // P = exp2(S) without the "- C" (one FADD less per score)
     case 41: PT_LAUNCH(8, 2, false, 1); break;
+    case 35: PT_LAUNCH(6, 2, false, 1); break;
+    case 38: PT_LAUNCH(12, 2, false, 1); break;
     case 42: PT_LAUNCH(4, 2, false, 1); break;
     case 43: PT_LAUNCH(3, 2, false, 1); break;
     case 46: PT_LAUNCH(0, 1, false, 1); break;

@@ -189,6 +189,120 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_kernel(LnParams p) {
   }
 }
 
+// ---------------------------------------------------------------- chained row kernel (b200_row_chain)
+template <int TPR, int VPT>
+__global__ void __launch_bounds__(ROW_THREADS) row_chain_kernel(b200_rowchain p) {
+  pdl_trigger();
+  pdl_wait();
+  const int rows_per_block = ROW_THREADS / TPR;
+  const long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / TPR;
+  const int t = threadIdx.x % TPR;
+  const int vecs = p.C >> 3;
+  const bool active = row < p.M;
+  const float invC = 1.f / (float)p.C;
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
+  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+  const int sample = active ? (int)((unsigned)row / (unsigned)(p.rows_per_sample > 0 ? p.rows_per_sample : 1)) : 0;
+  float v[VPT][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vv = t + i * TPR;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    if (active && vv < vecs) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * p.ldx + (vv << 3))), v[i]);
+      if (p.gate != nullptr) {
+        float g[8];
+        load8f(p.gate + (long long)sample * p.C + (vv << 3), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] *= g[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  if (p.norm1) {                                   // two-pass LayerNorm in fp32
+    const float mean = group_sum<TPR>(s) * invC;
+    float vs = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (t + i * TPR < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; vs += d * d; }
+      }
+    const float rstd = rsqrtf(group_sum<TPR>(vs) * invC + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int vv = t + i * TPR;
+      if (vv < vecs) {
+        float g[8];
+        load8f(p.norm1_g + (vv << 3), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * g[j];
+      }
+    }
+  }
+  float s2 = 0.f, ss2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vv = t + i * TPR;
+    if (active && vv < vecs) {
+      if (res != nullptr) {
+        float r[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(res + row * p.ldr + (vv << 3))), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+      }
+      if (p.out != nullptr) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (vv << 3)) = pack8(v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s2 += v[i][j]; ss2 += v[i][j] * v[i][j]; }
+    }
+  }
+  if (!p.norm2) return;
+  s2 = group_sum<TPR>(s2);
+  ss2 = group_sum<TPR>(ss2);
+  if (!active) return;
+  float m2 = 0.f, k2;
+  if (p.norm2 == 1) {
+    m2 = s2 * invC;
+    float vs = 0.f;                                // second pass for the variance: the values are in registers anyway
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (t + i * TPR < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - m2; vs += d * d; }
+      }
+    k2 = rsqrtf(group_sum<TPR>(vs) * invC + 1e-5f);
+  } else {
+    k2 = 1.f / fmaxf(sqrtf(ss2), 1e-12f);
+  }
+  const float* film = (p.norm2 == 2 && p.film != nullptr) ? p.film + (long long)sample * p.film_ld : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vv = t + i * TPR;
+    if (vv < vecs) {
+      const int c = vv << 3;
+      float g[8], f[8];
+      load8f(p.norm2_g + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (v[i][j] - m2) * k2 * g[j];
+      if (p.norm2 == 2) {
+        if (film != nullptr) {
+          float fs[8], fb[8];
+          load8f(film + c, fs);
+          load8f(film + p.C + c, fb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = f[j] * (fs[j] + 1.f) + fb[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_norm) + row * p.ld_norm + c) = pack8(f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- GlobalContext
 
 // logit[row] = x[row, :] . wk + bk   (GlobalContext.to_k, a 1x1 conv to one channel)
@@ -729,6 +843,28 @@ extern "C" int b200_layernorm(const void* x, int32_t ldx, const float* g, const 
   return B200_OK;
 }
 
+extern "C" int b200_row_chain(const b200_rowchain* pp, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B200_REQUIRE(pp != nullptr, "row_chain: null descriptor");
+  const b200_rowchain p = *pp;
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  B200_REQUIRE(p.x && p.M > 0 && p.M < (1ll << 31) && p.C > 0 && (p.C & 7) == 0 && (p.ldx & 7) == 0 && al16(p.x), "row_chain: bad input (C=%d)", p.C);
+  B200_REQUIRE(p.out != nullptr || p.norm2 != 0, "row_chain: no output");
+  B200_REQUIRE(p.out == nullptr || ((p.ldo & 7) == 0 && al16(p.out)), "row_chain: bad out");
+  B200_REQUIRE(p.residual == nullptr || ((p.ldr & 7) == 0 && al16(p.residual)), "row_chain: bad residual");
+  B200_REQUIRE(p.gate == nullptr || (p.rows_per_sample > 0 && al16(p.gate)), "row_chain: gate needs rows_per_sample and a 16-byte aligned table");
+  B200_REQUIRE((p.norm1 == 0 || p.norm1 == 1) && p.norm2 >= 0 && p.norm2 <= 2, "row_chain: bad norm kinds %d / %d", p.norm1, p.norm2);
+  B200_REQUIRE(p.norm1 == 0 || (p.norm1_g && al16(p.norm1_g)), "row_chain: norm1 gain");
+  B200_REQUIRE(p.norm2 == 0 || (p.norm2_g && al16(p.norm2_g) && p.out_norm && al16(p.out_norm) && (p.ld_norm & 7) == 0), "row_chain: norm2 operands");
+  B200_REQUIRE(p.film == nullptr || (p.norm2 == 2 && al16(p.film) && (p.film_ld & 3) == 0 && p.rows_per_sample > 0), "row_chain: FiLM operands");
+  const int vecs = p.C >> 3;
+  const int tpr = pick_tpr(vecs);
+  const int vpt = pick_vpt(vecs, tpr);
+  B200_REQUIRE(vpt <= MAX_VPT, "row_chain: C=%d too large", p.C);
+  DISPATCH_TPR(tpr, vpt, row_chain_kernel, p.M, p);
+  return B200_OK;
+}
+
 extern "C" int b200_gca_nchunk(int32_t rows_per_sample) {
   int n = rows_per_sample / 256;
   if (n < 1) n = 1;
@@ -736,9 +872,15 @@ extern "C" int b200_gca_nchunk(int32_t rows_per_sample) {
   return n;
 }
 
+static int gca_fused_bits() {
+  static const int fused = [] { const char* ev = getenv("B200_IMAGEN_GCA_FUSED"); return ev ? atoi(ev) : 0; }();
+  return fused;
+}
+
 extern "C" int b200_gca_chunks(int32_t rows_per_sample, int32_t C) {
+  if (!(gca_fused_bits() & 1)) return b200_gca_nchunk(rows_per_sample);   // stand-alone logits + pooling kernels: 256-pixel chunks
   int ppc = 256;
-  while (ppc > 8 && (long long)ppc * C * 2 > 128 * 1024) ppc >>= 1;   // the fused pooling kernel stages its pixel chunk in shared memory
+  while (ppc > 8 && (long long)ppc * C * 2 > 32 * 1024) ppc >>= 1;   // the fused pooling kernel stages its pixel chunk in shared memory (several CTAs per SM)
   int n = (rows_per_sample + ppc - 1) / ppc;
   return n < 1 ? 1 : n;
 }
@@ -759,25 +901,32 @@ extern "C" int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per
   float* partials = hid + (long long)B * hidden;
   float* logits = partials + (long long)B * nchunk * (C + 2);
   const long long M = (long long)B * rows_per_sample;
-  static const bool fused_on = [] { const char* ev = getenv("B200_IMAGEN_GCA_FUSED"); return ev == nullptr || atoi(ev) != 0; }();
+  // B200_IMAGEN_GCA_FUSED bits: 1 = fused logits + pooling kernel (pixel chunk staged once in shared memory), 2 = cluster kernel for
+  // combine + MLP + gate.  Default 0: the first version (128 KB chunks, one CTA per SM) measured 68 us per call vs 39 us for the five
+  // small kernels (profiles/r02_gca_fused_ab.txt).
+  const int fused = gca_fused_bits();
   const int ppc = (rows_per_sample + nchunk - 1) / nchunk;
   const size_t pool_smem = (size_t)ppc * C * 2 + (size_t)ppc * 4;
   const int hs = (hidden + GCA_CL - 1) / GCA_CL;
   const size_t tail_smem = ((size_t)GCA_TB * C + (size_t)GCA_TB * hs * GCA_CL + (size_t)GCA_TB * hs) * 4;
-  if (fused_on && pool_smem <= 160 * 1024 && tail_smem <= 160 * 1024 && (C & 3) == 0) {
-    // 2 launches: fused logits + pooling (pixel chunk staged once in shared memory), then the cluster kernel combine -> MLP -> gate
-    B200_SMEM_OPT_IN(gca_pool_fused_kernel, 200 * 1024);
+  const bool pool_fused = (fused & 1) && pool_smem <= 64 * 1024;
+  const bool tail_fused = (fused & 2) && tail_smem <= 160 * 1024 && (C & 3) == 0;
+  const int vecs = C >> 3;
+  const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
+  if (pool_fused) {
+    B200_SMEM_OPT_IN(gca_pool_fused_kernel, 64 * 1024);
     B200_CUDA_OK(b200_launch(gca_pool_fused_kernel, dim3(nchunk, B), dim3(GCA_THREADS), pool_smem, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                              rows_per_sample, C, wk, bk, nchunk, partials));
+  } else {
+    DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
+    B200_CUDA_OK(b200_launch(gca_pool_kernel, dim3(nchunk, B), dim3(GCA_THREADS), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials));
+  }
+  if (tail_fused) {
     B200_SMEM_OPT_IN(gca_tail_kernel, 200 * 1024);
     gca_tail_kernel<<<dim3(GCA_CL, (B + GCA_TB - 1) / GCA_TB), 256, tail_smem, st>>>(partials, nchunk, C, hidden, w1, b1, w2, b2, gate, B);
     B200_LAUNCH_OK();
     return B200_OK;
   }
-  const int vecs = C >> 3;
-  const int tpr = pick_tpr(vecs), vpt = pick_vpt(vecs, tpr);
-  DISPATCH_TPR(tpr, vpt, gca_logits_kernel, M, reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, wk, bk, logits, M);
-  B200_CUDA_OK(b200_launch(gca_pool_kernel, dim3(nchunk, B), dim3(GCA_THREADS), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows_per_sample, C, logits, nchunk, partials));
   B200_CUDA_OK(b200_launch(gca_combine_kernel, dim3((C + 255) / 256, B), dim3(256), 0, st, partials, nchunk, C, pooled));
   const int bg = (B + 7) / 8;
   B200_CUDA_OK(b200_launch(gca_mlp_kernel<8>, dim3((hidden * 32 + 255) / 256, bg), dim3(256), 0, st, pooled, w1, b1, hid, B, hidden, C, 1));

@@ -1887,9 +1887,12 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   {
     static const bool ks_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_CLUSTER_K"); return ev == nullptr || atoi(ev) != 0; }();
     const long long t256 = (long long)ntiles * (p.Npad / 256);
-    if (ks_on && !pair && !has_norm && ks <= 1 && p.Npad % 256 == 0 && gemm_is_simple(p) && e.l2_cols == 0 && t256 * 2 <= sm_count()) {
+    // measured on B200 (profiles/r02_gemm_clusterk_ab.txt): 8x8 conv 1024->1024 alone 65.5 -> 55.3 us, but inside the step only the K = 13824
+    // convs gain (78 -> 72 us); K = 4608 x N = 512 (32 tiles, 4-way split) got slower (31 -> 45 us): every CTA still streams its full share of
+    // the weights through L2 (19 TB/s demanded at 128 CTAs vs ~15 TB/s L2->SM) -> only very long K
+    if (ks_on && !pair && !has_norm && ks <= 1 && p.Npad % 256 == 0 && gemm_is_simple(p) && e.l2_cols == 0 && t256 * 2 <= sm_count() && total >= 192) {
       int split = (int)(sm_count() / t256);
-      if (split > 4) split = 4;
+      if (split > 2) split = 2;
       while (split > 1 && total / split < 16) --split;
       if (split >= 2) {
         // the B map of this path always has a 256-row box

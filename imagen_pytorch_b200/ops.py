@@ -6,7 +6,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import Src, Seg, Epilogue
+from ._lib import Src, Seg, Epilogue, RowChain
 
 BF16 = torch.bfloat16
 
@@ -100,6 +100,41 @@ class GemmCall:
 
     def __call__(self, stream):
         _lib.check(self.lib.b200_conv_gemm(*self.args, stream), 'b200_conv_gemm')
+
+
+class RowChainCall:
+    """Prebuilt b200_row_chain launch (gate -> LayerNorm -> + residual -> raw out; optional second norm -> out_norm).  Like GemmCall it can
+    take a consumer's norm later (the descriptor is read at launch time)."""
+
+    def __init__(self, x_ptr, ldx, M, Cc, *, gate=None, rows_per_sample=0, norm1_g=None, residual_ptr=None, ldr=0, out_ptr=None, ldo=0):
+        self.lib = _lib.load()
+        self.keep = [gate, norm1_g]
+        e = RowChain()
+        e.x, e.ldx, e.M, e.C = x_ptr, ldx, M, Cc
+        e.gate = gate.data_ptr() if gate is not None else None
+        e.rows_per_sample = rows_per_sample
+        e.norm1 = _lib.NORM_LN if norm1_g is not None else 0
+        e.norm1_g = norm1_g.data_ptr() if norm1_g is not None else None
+        e.residual, e.ldr = residual_ptr, ldr
+        e.out, e.ldo = out_ptr, ldo
+        self.e = e
+        self.args = (C.byref(e),)
+
+    def norm_capable(self):
+        return True
+
+    def set_norm2(self, kind, g, out_ptr, ld, *, film_ptr=None, film_ld=0, rows_per_sample=0):
+        assert self.e.norm2 == 0
+        self.keep.append(g)
+        e = self.e
+        e.norm2, e.norm2_g, e.out_norm, e.ld_norm = kind, g.data_ptr(), out_ptr, ld
+        e.film, e.film_ld = film_ptr, film_ld
+        if rows_per_sample:
+            assert e.rows_per_sample in (0, rows_per_sample)
+            e.rows_per_sample = rows_per_sample
+
+    def __call__(self, stream):
+        _lib.check(self.lib.b200_row_chain(*self.args, stream), 'b200_row_chain')
 
 
 def padded_bias(bias, N, device):

@@ -235,7 +235,9 @@ class UnetPlan:
     def _attach_norm(self, x: Rows, kind, gt, **film):
         """Try to let x's producer GEMM also emit norm(x): returns the normalised Rows or None."""
         c = x.call
-        if c is None or not self._fusable(x.C) or not c.norm_capable() or c.e.norm2 != 0:
+        if c is None or not self.fuse_norm or not c.norm_capable() or c.e.norm2 != 0:
+            return None
+        if isinstance(c, ops.GemmCall) and not self._fusable(x.C):             # a GEMM tile must span all channels; row kernels take any width
             return None
         out = self._new(x.rows, x.C, x.H, x.W)
         c.set_norm2(kind, gt, out.ptr, out.ld, **film)
@@ -265,10 +267,19 @@ class UnetPlan:
         return out
 
     def _layernorm(self, x: Rows, g, residual: Rows = None):
+        """LayerNorm(x) * g [+ residual] as a chained row kernel; a later consumer's norm may be attached to the same pass."""
         out = self._new(x.rows, x.C, x.H, x.W)
         gt = self._f32(g.flatten())
-        self._add('b200_layernorm', x.ptr, x.ld, gt.data_ptr(), None, 1e-5, residual.ptr if residual else None,
-                  residual.ld if residual else 0, out.ptr, out.ld, x.rows, x.C)
+        if not self.fuse_norm:
+            self._add('b200_layernorm', x.ptr, x.ld, gt.data_ptr(), None, 1e-5, residual.ptr if residual else None,
+                      residual.ld if residual else 0, out.ptr, out.ld, x.rows, x.C)
+            return out
+        rc = ops.RowChainCall(x.ptr, x.ld, x.rows, x.C, norm1_g=gt, residual_ptr=residual.ptr if residual else None,
+                              ldr=residual.ld if residual else 0, out_ptr=out.ptr, ldo=out.ld)
+        self._keep.append(rc)
+        self._ops.append((rc.lib.b200_row_chain, rc.args, 'b200_row_chain'))
+        if residual is not None:          # (a bare pre-norm output feeds a GEMM: nothing to attach to)
+            out.call = rc
         return out
 
     # ------------------------------------------------------------------ blocks
@@ -322,7 +333,13 @@ class UnetPlan:
                 self._gemm(srcs, segs, (R, Hc, Wc), self._pack(mats, dout), dout, r.t, ldc=r.ld, bias=br)
             else:
                 r = srcs[0]
-            self._add('b200_gate_residual', h3.ptr, h3.ld, gate.data_ptr(), r.ptr, r.ld, out.ptr, out.ld, M, dout, n)
+            if self.fuse_norm:
+                rc = ops.RowChainCall(h3.ptr, h3.ld, M, dout, gate=gate, rows_per_sample=n, residual_ptr=r.ptr, ldr=r.ld, out_ptr=out.ptr, ldo=out.ld)
+                self._keep.append(rc)
+                self._ops.append((rc.lib.b200_row_chain, rc.args, 'b200_row_chain'))
+                out.call = rc
+            else:
+                self._add('b200_gate_residual', h3.ptr, h3.ld, gate.data_ptr(), r.ptr, r.ld, out.ptr, out.ld, M, dout, n)
         elif has_res:
             # conv3x3(a2) + res_conv(x) accumulated in ONE implicit GEMM: 9 tap segments on a2 + 1x1 segments on the raw inputs
             segs = [(0, dh, dw) for (dh, dw) in self._conv_taps(3)]

@@ -183,6 +183,28 @@ int b200_layernorm(const void* x, int32_t ldx, const float* g, const float* beta
 int b200_gca_gate(const void* x, int32_t ldx, int B, int32_t rows_per_sample, int32_t C,
                   const float* wk, float bk, const float* w1, const float* b1, int32_t hidden,
                   const float* w2, const float* b2, float* scratch, int32_t nchunk, float* gate, void* stream);
+/* Chained per-row kernel: the per-pixel ops that sit between two GEMMs when the GEMM epilogue cannot host them (more than 256
+ * channels, or a producer that is not a GEMM), in ONE pass over the row:
+ *     v = x [* gate[row / rows_per_sample, :]]                      (GlobalContext gate, imagen_pytorch.py:754)
+ *     v = norm1 ? LayerNorm(v) * norm1_g : v                         (:331-349)
+ *     w = v + residual                         -> out  (bf16, may be NULL)
+ *     y = norm2 == 1 ? LayerNorm(w) * norm2_g : norm2 == 2 ? SiLU(RMSNorm(w) * norm2_g [* (scale+1) + shift])   -> out_norm
+ * The struct is read at launch time, so a consumer discovered later can attach its norm2 to an already recorded call.
+ * Replaces b200_layernorm (+ residual) / b200_gate_residual followed by b200_layernorm / b200_rmsnorm_film_silu. */
+typedef struct {
+  const void* x; int32_t ldx;
+  const float* gate;        /* fp32 [B, C] or NULL */
+  int32_t rows_per_sample;  /* rows per sample (selects the gate / film row) */
+  int32_t norm1; const float* norm1_g;
+  const void* residual; int32_t ldr;
+  void* out; int32_t ldo;
+  int32_t norm2; const float* norm2_g;
+  const float* film; int32_t film_ld;
+  void* out_norm; int32_t ld_norm;
+  int64_t M; int32_t C;
+} b200_rowchain;
+int b200_row_chain(const b200_rowchain* p, void* stream);
+
 int b200_gca_nchunk(int32_t rows_per_sample);
 /* chunk count for which b200_gca_gate takes its 2-launch path (fused logits + pooling with the pixel chunk staged in shared memory, then
  * one cluster kernel for combine + MLP + gate); the scratch layout is the same with this nchunk */

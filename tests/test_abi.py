@@ -35,5 +35,5 @@ def test_abi_version_and_npad_without_gpu():
 
 def test_struct_sizes_match_the_c_side():
     lib = _lib.load()
-    for which, struct in enumerate((_lib.Src, _lib.Seg, _lib.Epilogue, _lib.TimeRowJob, _lib.DdpmCoef, _lib.EdmCoef)):
+    for which, struct in enumerate((_lib.Src, _lib.Seg, _lib.Epilogue, _lib.TimeRowJob, _lib.DdpmCoef, _lib.EdmCoef, _lib.RowChain)):
         assert ctypes.sizeof(struct) == lib.b200_sizeof(which), struct.__name__

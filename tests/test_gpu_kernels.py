@@ -441,6 +441,56 @@ def test_layernorm_many_rows(Cc, residual, pitch):
     assert_close(out, ref, rtol=8e-3, atol=4e-3)
 
 
+@pytest.mark.parametrize('case', ['ln_res', 'gate_res', 'ln_res_ln', 'gate_res_rms_film', 'ln_res_rms_film_only', 'gate_res_ln_c40', 'ln_res_ln_c2048'])
+def test_row_chain_kernel(case):
+    """b200_row_chain: [gate] -> [LayerNorm] -> + residual -> raw out; [LayerNorm | RMSNorm+FiLM+SiLU] -> out_norm, in one pass over the row."""
+    cfg = {
+        'ln_res': dict(B=3, n=700, C=512, gate=False, n1=True, n2=0, film=False, raw=True),
+        'gate_res': dict(B=3, n=1024, C=128, gate=True, n1=False, n2=0, film=False, raw=True),
+        'ln_res_ln': dict(B=2, n=256, C=1024, gate=False, n1=True, n2=1, film=False, raw=True),
+        'gate_res_rms_film': dict(B=4, n=300, C=256, gate=True, n1=False, n2=2, film=True, raw=True),
+        'ln_res_rms_film_only': dict(B=2, n=64, C=1024, gate=False, n1=True, n2=2, film=True, raw=False),
+        'gate_res_ln_c40': dict(B=3, n=77, C=40, gate=True, n1=False, n2=1, film=False, raw=True),
+        'ln_res_ln_c2048': dict(B=2, n=33, C=2048, gate=False, n1=True, n2=1, film=False, raw=True),
+    }[case]
+    B, n, Cc = cfg['B'], cfg['n'], cfg['C']
+    M = B * n
+    x = rnd(M, Cc, seed=1).to(BF16)
+    res = (rnd(M, Cc, seed=2) * 1.3 + 0.2).to(BF16)
+    gate = torch.sigmoid(rnd(B, Cc, seed=3)).contiguous() if cfg['gate'] else None
+    g1 = (1 + 0.2 * rnd(Cc, seed=4)).contiguous()
+    g2 = (1 + 0.2 * rnd(Cc, seed=5)).contiguous()
+    film = rnd(B, 2 * Cc + 8, scale=0.3, seed=6).contiguous() if cfg['film'] else None
+    out = torch.zeros(M, Cc, dtype=BF16, device=DEV) if cfg['raw'] else None
+    out_n = torch.zeros(M, Cc, dtype=BF16, device=DEV) if cfg['n2'] else None
+    call = ops.RowChainCall(x.data_ptr(), Cc, M, Cc, gate=gate, rows_per_sample=n, norm1_g=g1 if cfg['n1'] else None, residual_ptr=res.data_ptr(), ldr=Cc,
+                            out_ptr=out.data_ptr() if out is not None else None, ldo=Cc)
+    if cfg['n2']:
+        g2k = (g2 * math.sqrt(Cc)).contiguous() if cfg['n2'] == 2 else g2
+        call.set_norm2(cfg['n2'], g2k, out_n.data_ptr(), Cc, film_ptr=film.data_ptr() if film is not None else None,
+                       film_ld=film.shape[1] if film is not None else 0, rows_per_sample=n)
+    call(stream())
+    torch.cuda.synchronize()
+    v = x.float()
+    if gate is not None:
+        v = v * gate.repeat_interleave(n, 0)
+    if cfg['n1']:
+        v = _ln_ref(v, g1)
+    w = v + res.float()
+    if out is not None:
+        assert_close(out, w, 8e-3, 8e-3, f'{case}: raw')
+    if cfg['n2']:
+        if cfg['n2'] == 1:
+            y = _ln_ref(w, g2)
+        else:
+            y = F.normalize(w, dim=-1) * g2 * math.sqrt(Cc)
+            if film is not None:
+                fr = film.repeat_interleave(n, dim=0)
+                y = y * (fr[:, :Cc] + 1) + fr[:, Cc:2 * Cc]
+            y = F.silu(y)
+        assert_close(out_n, y, 1.2e-2, 1.2e-2, f'{case}: normalised')
+
+
 @pytest.mark.parametrize('n,Cc,B', [(4096, 128, 3), (64, 1024, 3), (300, 40, 3), (256, 512, 11), (1024, 256, 32), (16, 2048, 9)])
 def test_global_context_gate_and_gate_residual(n, Cc, B):
     hid = max(3, Cc // 2)
