@@ -52,7 +52,6 @@ struct GemmParams {
   int nseg, total_chunks, ntiles_m;
   int ksplit;      // > 1: K is split over ksplit adjacent work items; each writes its raw fp32 partial tile to out + split * M * ldc
   int tma_store;   // staged epilogue hands each 32-row x 32-column group to a TMA store (plain bf16 row-major destinations)
-  uint32_t wait_ns;   // suspend-time hint of the producer / issuer barrier waits (0 = plain spin); B200_IMAGEN_GEMM_WAIT_NS
   int debug;   // B200_IMAGEN_GEMM_DEBUG bit mask (bottleneck experiments only): 1 skip epilogue work, 2 skip MMA issue, 4 skip TMA loads, 8 no wait before restaging (WRONG results), 16 no proxy fence (WRONG results)
   int nchunks[B200_MAX_SRC];
   SegDev seg[B200_MAX_SEG];
@@ -790,7 +789,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
             if (kc < kc0 || kc >= kc1) continue;   // another split's share of K
-            mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
             if (p.debug & 4) {
               mbar_arrive(&full_bar[stage]);
             } else {
@@ -812,13 +811,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1u, p.wait_ns);   // epilogue has drained this accumulator stage
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         const int split = t % ksplit;
         const int nkc = (split + 1) * p.total_chunks / ksplit - split * p.total_chunks / ksplit;
         for (int kc = 0; kc < nkc; ++kc) {
-          mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
@@ -856,7 +855,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int tile = (int)((unsigned)tt / (unsigned)n_tiles_n), n0 = (tt - tile * n_tiles_n) * BN;
       RowInfo ri = tile_row(p, tile, rit);
       if (p.ksplit > 1) ri.orow += (long long)split * p.B * p.H * p.W;   // partial tiles: [split][row][col] fp32
-      mbar_wait_sleep(&tmem_full_bar[acc], acc_phase, p.wait_ns);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * BNH);
       if (!(p.debug & 1)) {
@@ -1133,7 +1132,7 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         const int nch = p.nchunks[src];
         for (int cc = 0; cc < nch; ++cc, ++kc) {
           if (kc < kc0 || kc >= kc1) continue;
-          mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_expect_tx(&full_bar[stage], KS_STAGE_BYTES);
           uint8_t* sA = smem + stage * KS_STAGE_BYTES;
           tma_load_4d(sA, mA, &full_bar[stage], cc * BK, w0 + dw, h0 + dh, b0);
@@ -1148,7 +1147,7 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < kc1 - kc0; ++kc) {
-        mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * KS_STAGE_BYTES);
         const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
@@ -1163,7 +1162,7 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   } else if (rank != 0) {
     // ---------------- non-zero ranks: accumulator -> own shared memory (row = thread, KS_PITCH floats per row)
     const int q = warp & 3, half = (warp - 2) >> 2;
-    mbar_wait_sleep(tmem_full_bar, 0, p.wait_ns);          // every MMA of this CTA has completed: the operand ring is free
+    mbar_wait(tmem_full_bar, 0);          // every MMA of this CTA has completed: the operand ring is free
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BNH);
     float* row = parked + (size_t)(q * 32 + lane) * KS_PITCH + half * BNH;
@@ -1182,7 +1181,7 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     // ---------------- rank 0: the normal staged epilogue over (own accumulator + parked partials of ranks 1..nsplit-1, in rank order)
     const int q = warp & 3, half = (warp - 2) >> 2;
     const RowInfo ri = tile_row(p, tile, row_in_tile(p, q * 32 + lane));
-    mbar_wait_sleep(tmem_full_bar, 0, p.wait_ns);
+    mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BNH);
     const uint32_t my_row = smem_u32(parked + (size_t)(q * 32 + lane) * KS_PITCH + half * BNH);
@@ -1289,7 +1288,7 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           const int dh = p.seg[s].dh, dw = p.seg[s].dw;
           const int nch = p.nchunks[src];
           for (int cc = 0; cc < nch; ++cc, ++kc) {
-            mbar_wait_sleep(&empty_bar[stage], phase ^ 1u, p.wait_ns);
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_expect_tx(&full_bar[stage], T_STAGE_BYTES);
             uint8_t* sW = smem + stage * T_STAGE_BYTES;
             tma_load_2d(sW, &mapW, &full_bar[stage], kc * BK, 0);
@@ -1306,11 +1305,11 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait_sleep(&tmem_empty_bar[acc], acc_phase ^ 1u, p.wait_ns);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T_BP);
         for (int kc = 0; kc < p.total_chunks; ++kc) {
-          mbar_wait_sleep(&full_bar[stage], phase, p.wait_ns);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t w_addr = smem_u32(smem + stage * T_STAGE_BYTES);
           const uint64_t adesc = make_sw128_kmajor_desc(w_addr);
@@ -1341,7 +1340,7 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait_sleep(&tmem_full_bar[acc], acc_phase, p.wait_ns);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T_BP + grp * 128);
 #pragma unroll 1
@@ -1666,8 +1665,6 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   {
     static const int dbg = [] { const char* e = getenv("B200_IMAGEN_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
-    static const uint32_t wns = [] { const char* e = getenv("B200_IMAGEN_GEMM_WAIT_NS"); return (uint32_t)(e ? atoi(e) : 0); }();
-    p.wait_ns = wns;
   }
   for (int i = 0; i < nsrc; ++i) {
     B200_REQUIRE(srcs[i].ptr != nullptr && srcs[i].C > 0, "conv_gemm: src %d empty", i);
