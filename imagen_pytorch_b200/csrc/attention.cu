@@ -376,6 +376,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) cross_attn_fewkeys_kernel(Attn
 int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
                       int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, float max_logit, cudaStream_t st);
 
+int b200_cross_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
+                            int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, cudaStream_t st);
+
 extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k,
                               const void* v, int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads,
                               float max_logit, void* stream) {
@@ -398,6 +401,12 @@ extern "C" int b200_attention(const void* q, void* o, int64_t q_bs, int64_t q_hs
   p.v = reinterpret_cast<const __nv_bfloat16*>(v);
   p.q_bs = q_bs; p.q_hs = q_hs; p.kv_bs = kv_bs; p.kv_hs = kv_hs;
   p.q_rs = q_rs; p.kv_rs = kv_rs; p.rows = rows; p.n_keys = n_keys;
+  // <= 64 keys, heads adjacent in q / k / v (the CrossAttention layout), bounded logits: persistent tcgen05 kernel
+  if (n_keys <= 64 && max_logit > 0.f && max_logit <= 40.f && n_heads >= 1 && n_heads <= 8 && q_hs == 64 && kv_hs == 64 && q_rs == n_heads * 64 &&
+      kv_rs == n_heads * 64 && (long long)rows >= 128) {
+    static const bool tc_on = [] { const char* e = getenv("B200_IMAGEN_XATTN_TC"); return e == nullptr || atoi(e) != 0; }();
+    if (tc_on) return b200_cross_attention_tc(q, o, q_bs, q_hs, q_rs, rows, k, v, kv_bs, kv_hs, kv_rs, n_keys, B, n_heads, st);
+  }
   if (n_keys <= ATT_BN) {
     static const bool on = [] { const char* e = getenv("B200_IMAGEN_XATTN_FEWKEYS"); return e == nullptr || atoi(e) != 0; }();
     if (on) {

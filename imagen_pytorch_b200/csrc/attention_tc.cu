@@ -539,7 +539,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)  (P: 64 keys per 32 columns).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int PT_STAGES = 5;
-constexpr int PT_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 256 + 2048;   // + barriers + row-sum exchange
+constexpr int PT_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 512 + 2048;   // + barriers + row-sum exchange
 
 // 32 scores -> 16 packed bf16x2 probabilities + row-sum contribution.  MODE bit 0: no "- C" (P = exp2(S) directly: the bound only
 // has to keep 2^C * n_keys inside fp32, and O / l is invariant to the common factor 2^C -- one FADD less per score); bits 1-2 are
@@ -590,14 +590,20 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   uint64_t* kv_empty = kv_full + PT_STAGES;             // [PT_STAGES] (count 2: both groups' P V MMAs)
   uint64_t* s_full = kv_empty + PT_STAGES;              // [group]
   uint64_t* s_empty = s_full + 2;                       // [group]
-  uint64_t* p_full = s_empty + 2;                       // [group][half]
-  uint64_t* p_empty = p_full + 4;                       // [group][half]
-  uint64_t* o_full = p_empty + 4;                       // [group]
+  uint64_t* p_full = s_empty + 2;                       // [group][half][32-key chunk]
+  uint64_t* p_empty = p_full + 8;                       // [group][half][32-key chunk]
+  uint64_t* o_full = p_empty + 8;                       // [group]
   uint64_t* order_bar = o_full + 2;                     // [group]: group g may start exponentiating its next tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(order_bar + 2);
-  float* sL = reinterpret_cast<float*>(bars + 32);      // [group][sub][128] partial row sums
-  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 2 + 1 <= 32, "barrier block is 256 bytes");
+  float* sL = reinterpret_cast<float*>(bars + 64);      // [group][sub][128] partial row sums
+  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 8 + 8 + 2 + 2 + 1 <= 64, "barrier block is 512 bytes");
 
+  // MODE bit 3: one mbarrier arrival per softmax WARP (elected lane after __syncwarp) instead of one per thread: 128-256 arrivals
+  // on one shared-memory word serialise in the barrier unit, and every one of them sits on the S -> P -> O dependency chain
+  constexpr bool WARP_ARRIVE = (MODE & 8) != 0;
+  // MODE bit 5: P handed to the MMA issuer in 32-key chunks (own full / empty barrier each) instead of 64-key halves: the chunk a warp
+  // writes first was multiplied while it exponentiated its second chunk of the previous tile, so it never waits for the P V MMA
+  constexpr bool PCH = (MODE & 32) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * (2 * FA_BM);
   const int h = blockIdx.y, b = blockIdx.z;
@@ -613,10 +619,10 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
     for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_empty[g], 128 * SUB);
+      mbar_init(&s_empty[g], WARP_ARRIVE ? 4 * SUB : 128 * SUB);
       mbar_init(&o_full[g], 1);
       mbar_init(&order_bar[g], 4 * SUB);                // one arrival per softmax warp of the OTHER group
-      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }
+      for (int i = 0; i < 4; ++i) { mbar_init(&p_full[4 * g + i], WARP_ARRIVE ? 4 : 128); mbar_init(&p_empty[4 * g + i], 1); }
     }
     fence_barrier_init();
   }
@@ -674,17 +680,19 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         if (j + 1 < ntiles) issue_s(j + 1);
         const int st = j % PT_STAGES;
         const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
-        for (int hf = 0; hf < 2; ++hf) {        // the first 64 keys are multiplied while the second 64 are exponentiated
-          if (hf == 1 && dead1 && j == ntiles - 1) break;
-          const int pb = 2 * g + hf;
+        // the first keys are multiplied while the later ones are exponentiated: halves in order, or (PCH) chunk 0 of both halves first
+        for (int u = 0; u < (PCH ? 4 : 2); ++u) {
+          const int hf = !PCH ? u : (SUB == 2 ? (u & 1) : (u >> 1)), ci = !PCH ? 0 : (SUB == 2 ? (u >> 1) : (u & 1));   // production order
+          if (hf == 1 && dead1 && j == ntiles - 1) continue;
+          const int pb = 4 * g + 2 * hf + ci;
           mbar_wait_sleep(&p_full[pb], (uint32_t)(j & 1), p.wait_ns);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = (PCH ? 2 * ci : 0); k < (PCH ? 2 * ci + 2 : 4); ++k) {
             // A: 16 keys = 8 packed columns of this half's P block; B: 16 key rows of V (MN-major, 2 KB)
             const uint32_t a_tmem = tmem_base + TM_P + (uint32_t)(g * 64 + hf * 32 + k * 8);
             const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((hf * 4 + k) * 16 * 128), 1024, 1024);
-            umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, (j | hf | k) != 0 ? 1u : 0u);
+            umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, (j | u | (k & 1) | (PCH ? 0 : k)) != 0 ? 1u : 0u);
           }
           umma_commit(&p_empty[pb]);
         }
@@ -719,12 +727,12 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       mbar_wait_sleep(&s_full[g], (uint32_t)(j & 1), p.wait_ns);
       tc_fence_after();
       bool have_token = !ORDER;
-      constexpr int CH = SUB == 2 ? 32 : 64;
+      constexpr int CH = (SUB == 2 && !(MODE & 16)) ? 32 : 64;   // MODE bit 4: all 64 scores of the thread in registers before the first exponential (S freed earlier)
 #pragma unroll 1
       for (int hh = 0; hh < 2 / SUB; ++hh) {
         const int hf = SUB == 2 ? sub : hh;
         if (hf == 1 && last_dead) break;
-        const int pb = 2 * g + hf;
+        const int pb = 4 * g + 2 * hf;
         const uint32_t p_col = tmem_base + lane_off + TM_P + (uint32_t)(g * 64 + hf * 32);
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += CH) {
@@ -740,10 +748,11 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
           for (int i = 0; i < CH; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
           if (c0 + CH == 64 && (SUB == 2 || hh == 1 || last_dead)) {
-            tc_fence_before();
-            mbar_arrive(&s_empty[g]);           // this thread's share of S_g is in registers
+            tc_fence_before();                  // this thread's share of S_g is in registers
+            if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&s_empty[g]); }
+            else mbar_arrive(&s_empty[g]);
           }
-          if (c0 == 0) {
+          if (!PCH && c0 == 0) {
             mbar_wait_sleep(&p_empty[pb], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // the P V MMAs of tile j-1 have finished reading this half of P
             tc_fence_after();
           }
@@ -757,16 +766,29 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             const int kb = key0 + hf * 64 + c0 + 32 * t;
             if (ragged) pt_chunk32<POLY, MODE, true>(sr + 32 * t, C, kb, p.n_keys, pk, l);
             else pt_chunk32<POLY, MODE, false>(sr + 32 * t, C, kb, p.n_keys, pk, l);
+            if (PCH) {
+              mbar_wait_sleep(&p_empty[pb + ((c0 + 32 * t) >> 5)], (uint32_t)((j & 1) ^ 1), p.wait_ns);
+              tc_fence_after();
+            }
             tmem_st16(p_col + (uint32_t)((c0 + 32 * t) >> 1), pk);
+            if (PCH) {
+              tmem_st_wait();
+              tc_fence_before();
+              if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&p_full[pb + ((c0 + 32 * t) >> 5)]); }
+              else mbar_arrive(&p_full[pb + ((c0 + 32 * t) >> 5)]);
+            }
           }
         }
         if (ORDER && (SUB == 2 || hh == 1 || last_dead)) {   // exponentials of this tile issued: the other group's turn
           __syncwarp();
           if (lane == 0) mbar_arrive(&order_bar[g ^ 1]);
         }
-        tmem_st_wait();                          // the stores have landed in tensor memory ...
-        tc_fence_before();                       // ... and are ordered before the issuer's MMAs through the barrier
-        mbar_arrive(&p_full[pb]);
+        if (!PCH) {
+          tmem_st_wait();                        // the stores have landed in tensor memory ...
+          tc_fence_before();                     // ... and are ordered before the issuer's MMAs through the barrier
+          if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&p_full[pb]); }
+          else mbar_arrive(&p_full[pb]);
+        }
       }
     }
     // ---- O / l -> global (with SUB == 2 the two column-half threads of a row add their sums and each stores 32 channels)
@@ -808,6 +830,220 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Few-keys (cross-) attention on tcgen05: <= 64 keys per head (the 39 context rows of CrossAttention).  The work is memory bound
+// (q in, o out: 268 MB at the 64x64 level), so the kernel is PERSISTENT: one CTA per SM walks a contiguous range of work items
+// (sample b, 128-row query tile, head h); the K and V rows of all heads of the current sample stay resident in shared memory
+// (2 x 64 KB, reloaded when b changes), Q tiles stream through a 4-stage TMA ring, and three TMEM "slots" (S 64 + P 32 + O 64 columns)
+// keep three items in flight:   S = Q K_h^T  (M128 x N64 x K64)  ->  4 worker warps: tcgen05.ld, P = exp2(S) (bounded cosine-sim logits,
+// keys >= n_keys masked), row sum, P -> tensor memory  ->  O = P V_h  (A operand from TMEM)  ->  same warps: O / l -> bf16 -> one
+// 128-byte row store per thread.  Replaces the mma.sync kernel (2.3 TB/s; its mma.sync + MUFU work alone is ~45 us per launch).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int XA_NS = 3;                           // TMEM slots / items in flight
+constexpr int XA_QS = 4;                           // Q ring stages
+constexpr int XA_KEYS = 64;                        // key tile (rows beyond n_keys are zero-filled by TMA and masked)
+constexpr int XA_KV_HEAD_BYTES = XA_KEYS * 64 * 2; // one head's K (or V) tile: 8 KB
+constexpr int XA_MAX_HEADS = 8;
+constexpr int XA_SMEM = XA_QS * FA_Q_BYTES + 2 * XA_MAX_HEADS * XA_KV_HEAD_BYTES + 1024 + 512;
+
+struct XaParams {
+  __nv_bfloat16* o;
+  long long q_bs;          // elements between samples in q / o
+  int q_rs, q_hs;          // row / head strides of q and o (elements)
+  int rows, n_keys, B, heads;
+  int tiles_per_sample;    // ceil(rows / 128)
+  int items_per_cta;
+  uint32_t wait_ns;
+};
+
+__global__ void __launch_bounds__(64 + 128 * XA_NS, 1)
+cross_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                     const __grid_constant__ XaParams p) {
+  pdl_trigger();
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                        // [XA_QS] query tiles
+  uint8_t* sK = sQ + XA_QS * FA_Q_BYTES;                     // [heads] K tiles of the current sample
+  uint8_t* sV = sK + XA_MAX_HEADS * XA_KV_HEAD_BYTES;        // [heads] V tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + XA_MAX_HEADS * XA_KV_HEAD_BYTES);
+  uint64_t* q_full = bars;                       // [XA_QS]
+  uint64_t* q_empty = q_full + XA_QS;            // [XA_QS]
+  uint64_t* kv_full = q_empty + XA_QS;           // [1]
+  uint64_t* kv_empty = kv_full + 1;              // [1]
+  uint64_t* s_full = kv_empty + 1;               // [XA_NS]
+  uint64_t* p_full = s_full + XA_NS;             // [XA_NS]
+  uint64_t* o_full = p_full + XA_NS;             // [XA_NS]
+  uint64_t* slot_free = o_full + XA_NS;          // [XA_NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + XA_NS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_items = (long long)p.B * p.tiles_per_sample * p.heads;
+  const long long item0 = (long long)blockIdx.x * p.items_per_cta;
+  const long long item1 = item0 + p.items_per_cta < total_items ? item0 + p.items_per_cta : total_items;
+  const int n_items = item1 > item0 ? (int)(item1 - item0) : 0;
+  const int per_sample = p.tiles_per_sample * p.heads;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    for (int s = 0; s < XA_QS; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int s = 0; s < XA_NS; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);       // one arrival per worker warp of the slot
+      mbar_init(&o_full[s], 1);
+      mbar_init(&slot_free[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  // TMEM columns: accumulators on 64-column boundaries (S_s at 128 s, O_s at 128 s + 64), the packed P tiles behind them (384 + 32 s)
+  constexpr uint32_t SLOT_COLS = 128, P_BASE = 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: K/V of all heads whenever the sample changes, then one Q tile per item
+      int cur_b = -1, epoch = 0;
+      for (int i = 0; i < n_items; ++i) {
+        const long long it = item0 + i;
+        const int b = (int)(it / per_sample), rem = (int)(it % per_sample);
+        const int tile = rem / p.heads, h = rem % p.heads;
+        if (b != cur_b) {
+          mbar_wait_sleep(kv_empty, (uint32_t)((epoch & 1) ^ 1), p.wait_ns);      // every MMA that read the previous sample's K/V has completed
+          mbar_expect_tx(kv_full, (uint32_t)(2 * p.heads * XA_KV_HEAD_BYTES));
+          for (int hh = 0; hh < p.heads; ++hh) {
+            tma_load_4d(sK + hh * XA_KV_HEAD_BYTES, &mapK, kv_full, 0, hh, 0, b);
+            tma_load_4d(sV + hh * XA_KV_HEAD_BYTES, &mapV, kv_full, 0, hh, 0, b);
+          }
+          cur_b = b;
+          ++epoch;
+        }
+        const int st = i % XA_QS;
+        mbar_wait_sleep(&q_empty[st], (uint32_t)(((i / XA_QS) & 1) ^ 1), p.wait_ns);
+        mbar_expect_tx(&q_full[st], FA_Q_BYTES);
+        tma_load_4d(sQ + st * FA_Q_BYTES, &mapQ, &q_full[st], 0, h, tile * FA_BM, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(XA_KEYS >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      int epoch = 0, kv_b = -1;
+      auto item_b = [&](int i) { return (int)((item0 + i) / per_sample); };
+      auto item_h = [&](int i) { return (int)((item0 + i) % p.heads); };   // per_sample is a multiple of heads
+      auto issue_s = [&](int i) {
+        const int b = item_b(i), h = item_h(i), st = i % XA_QS, slot = i % XA_NS;
+        if (b != kv_b) {
+          mbar_wait_sleep(kv_full, (uint32_t)(epoch & 1), p.wait_ns);
+          kv_b = b;
+          ++epoch;
+        }
+        mbar_wait_sleep(&q_full[st], (uint32_t)((i / XA_QS) & 1), p.wait_ns);
+        mbar_wait_sleep(&slot_free[slot], (uint32_t)(((i / XA_NS) & 1) ^ 1), p.wait_ns);   // the workers have stored the item that used this slot
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ + st * FA_Q_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sK + h * XA_KV_HEAD_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(slot * SLOT_COLS), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[slot]);
+        umma_commit(&q_empty[st]);
+      };
+      if (n_items > 0) issue_s(0);
+      for (int i = 0; i < n_items; ++i) {
+        const bool next_same_sample = i + 1 < n_items && item_b(i + 1) == item_b(i);
+        if (next_same_sample) issue_s(i + 1);              // scores of the next item while the workers exponentiate this one
+        const int slot = i % XA_NS, h = item_h(i);
+        mbar_wait_sleep(&p_full[slot], (uint32_t)((i / XA_NS) & 1), p.wait_ns);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + h * XA_KV_HEAD_BYTES);
+#pragma unroll
+        for (int k = 0; k < XA_KEYS / 16; ++k) {
+          const uint32_t a_tmem = tmem_base + P_BASE + (uint32_t)(slot * 32 + k * 8);
+          const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)(k * 16 * 128), 1024, 1024);
+          umma_bf16_ts(tmem_base + (uint32_t)(slot * SLOT_COLS + 64), a_tmem, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[slot]);
+        if (i + 1 < n_items && !next_same_sample) {
+          umma_commit(kv_empty);                            // all MMAs of this sample are issued: its K/V may be replaced once they complete
+          issue_s(i + 1);
+        }
+      }
+    }
+  } else {
+    // ---------------- workers: slot = (warp - 2) / 4, thread = one query row of every item of its slot
+    const int slot = (warp - 2) >> 2;
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + (uint32_t)(slot * SLOT_COLS);
+    const uint32_t t_p = tmem_base + lane_off + P_BASE + (uint32_t)(slot * 32);
+    for (int i = slot; i < n_items; i += XA_NS) {
+      const long long it = item0 + i;
+      const int b = (int)(it / per_sample), rem = (int)(it % per_sample);
+      const int tile = rem / p.heads, h = rem % p.heads;
+      const uint32_t par = (uint32_t)((i / XA_NS) & 1);
+      mbar_wait_sleep(&s_full[slot], par, p.wait_ns);
+      tc_fence_after();
+      float l = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < XA_KEYS; c0 += 32) {
+        uint32_t sr[32], pk[16];
+        tmem_ld32_nowait(t_s + (uint32_t)c0, sr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(sr[j]));
+        pt_chunk32<0, 1, true>(sr, 0.f, c0, p.n_keys, pk, l);
+        tmem_st16(t_p + (uint32_t)(c0 >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[slot]);
+      mbar_wait_sleep(&o_full[slot], par, p.wait_ns);
+      tc_fence_after();
+      const float inv = 1.f / l;
+      const int row = tile * FA_BM + r;
+      __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)row * p.q_rs + (long long)h * p.q_hs;
+#pragma unroll
+      for (int c0 = 0; c0 < FA_D; c0 += 32) {
+        uint32_t orr[32];
+        tmem_ld32_nowait(t_s + 64u + (uint32_t)c0, orr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(orr[j]));
+        if (row < p.rows) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * t) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[slot]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 // 4-D map over [B][rows x heads][64]: dim0 = 64 head channels, dims 1/2 = (rows, heads) ordered by ascending stride
 // (heads_first: the 8 heads of a row are adjacent, as in the cross-attention q / k / v layout), dim3 = batch.
 int encode_rows_map(CUtensorMap* map, const void* base, int rows, int n_heads, int B, long long rs, long long hs, long long bs, int box_rows,
@@ -837,6 +1073,33 @@ int encode_rows_map(CUtensorMap* map, const void* base, int rows, int n_heads, i
 }
 
 }  // namespace
+
+// called by b200_attention (attention.cu) for <= 64 keys with a usable logit bound and heads-adjacent layouts
+int b200_cross_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
+                            int64_t kv_bs, int64_t kv_hs, int32_t kv_rs, int32_t n_keys, int B, int n_heads, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = encode_rows_map(&mq, q, rows, n_heads, B, q_rs, q_hs, q_bs, FA_BM, true, "Q")) != B200_OK) return rc;
+  if ((rc = encode_rows_map(&mk, k, n_keys, n_heads, B, kv_rs, kv_hs, kv_bs, XA_KEYS, true, "K")) != B200_OK) return rc;
+  if ((rc = encode_rows_map(&mv, v, n_keys, n_heads, B, kv_rs, kv_hs, kv_bs, XA_KEYS, true, "V")) != B200_OK) return rc;
+  XaParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.q_bs = q_bs; p.q_rs = q_rs; p.q_hs = (int)q_hs; p.rows = rows; p.n_keys = n_keys; p.B = B; p.heads = n_heads;
+  p.tiles_per_sample = (rows + FA_BM - 1) / FA_BM;
+  const long long total = (long long)B * p.tiles_per_sample * n_heads;
+  const int sms = sm_count();
+  long long per = (total + sms - 1) / sms;
+  per = (per + n_heads - 1) / n_heads * n_heads;                 // whole query tiles per CTA: the K/V reload boundaries fall between tiles
+  p.items_per_cta = (int)per;
+  {
+    static const uint32_t wns = [] { const char* ev = getenv("B200_IMAGEN_FA_WAIT_NS"); return (uint32_t)(ev ? atoi(ev) : FA_DEFAULT_WAIT_NS); }();
+    p.wait_ns = wns;
+  }
+  const int grid = (int)((total + per - 1) / per);
+  B200_SMEM_OPT_IN(cross_attn_tc_kernel, XA_SMEM);
+  B200_CUDA_OK(b200_launch(cross_attn_tc_kernel, dim3(grid), dim3(64 + 128 * XA_NS), XA_SMEM, st, mq, mk, mv, p));
+  return B200_OK;
+}
 
 // called by b200_attention (attention.cu) when the caller supplies a usable logit bound
 int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_t q_rs, int32_t rows, const void* k, const void* v,
@@ -911,6 +1174,17 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 49: PT_LAUNCH(5, 1, false, 1); break;
     case 44: PT_LAUNCH(6, 1, false, 1); break;
     case 45: PT_LAUNCH(8, 1, false, 1); break;
+    case 53: PT_LAUNCH(0, 2, false, 9); break;   // one barrier arrival per warp
+    case 54: PT_LAUNCH(8, 2, false, 9); break;
+    case 55: PT_LAUNCH(4, 2, false, 9); break;
+    case 56: PT_LAUNCH(4, 1, false, 9); break;
+    case 57: PT_LAUNCH(0, 2, false, 15); break;
+    case 58: PT_LAUNCH(8, 2, false, 25); break;  // warp arrivals + both 32-score chunks preloaded
+    case 59: PT_LAUNCH(8, 2, false, 17); break;  // preload only
+    case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
+    case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
+    case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only
+    case 63: PT_LAUNCH(4, 1, false, 41); break;  // 8 softmax warps: warp arrivals + chunks  // bottleneck experiment: warp arrivals, neither MUFU nor TMEM reads
     case 50: PT_LAUNCH(0, 2, false, 3); break;   // bottleneck experiment: no MUFU
     case 51: PT_LAUNCH(0, 2, false, 5); break;   // bottleneck experiment: no TMEM reads
     case 52: PT_LAUNCH(0, 2, false, 7); break;   // bottleneck experiment: neither

@@ -360,6 +360,25 @@ def test_cross_attention_layout_per_head_kv(n, nk, path):
     assert_close(o, ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('B,n,nk,heads', [(600, 128, 39, 8), (37, 200, 39, 4), (3, 4096, 17, 8)])
+def test_cross_attention_tc_many_samples_per_cta(B, n, nk, heads):
+    """Persistent tcgen05 cross-attention (cross_attn_tc_kernel): a CTA's item range spans several samples (its resident K/V tiles are
+    reloaded at every sample boundary), partial last query tiles, fewer than 8 heads."""
+    inner = heads * 64
+    q = (F.normalize(rnd(B, n, heads, 64), dim=-1) * 8 * 1.4426950408889634).to(BF16)
+    k = F.normalize(rnd(B, nk, heads, 64, seed=1), dim=-1).to(BF16)
+    v = rnd(B, nk, heads, 64, seed=2).to(BF16)
+    o = torch.zeros_like(q)
+    _lib.call('b200_attention', q.data_ptr(), o.data_ptr(), n * inner, 64, inner, n, k.data_ptr(), v.data_ptr(), nk * inner, 64, inner, nk, B, heads,
+              BOUND, stream())
+    torch.cuda.synchronize()
+    qq = q.permute(0, 2, 1, 3).reshape(B * heads, n, 64)
+    kk = k.permute(0, 2, 1, 3).reshape(B * heads, nk, 64)
+    vv = v.permute(0, 2, 1, 3).reshape(B * heads, nk, 64)
+    ref = ref_attention(qq, kk, vv).view(B, heads, n, 64).permute(0, 2, 1, 3)
+    assert_close(o, ref, rtol=1e-2, atol=1e-2)
+
+
 # ------------------------------------------------------------------------------------------------ row-wise kernels
 
 @pytest.mark.parametrize('Cs,film', [([128], True), ([256, 128], False), ([1536, 768], True), ([32], False), ([40, 24], True)])
