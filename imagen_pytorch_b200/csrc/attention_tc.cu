@@ -28,7 +28,7 @@ constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_DEFAULT_VARIANT = 41;   // ping-pong, P in tensor memory, 16 softmax warps, P = exp2(S), 1/8 of the exp2 on the FMA pipe
+constexpr int FA_DEFAULT_VARIANT = 65;   // ping-pong, P in tensor memory, 16 softmax warps, all 64 scores of a thread preloaded (S freed at once), P = exp2(S), 1/6 of the exp2 on the FMA pipe
 constexpr int FA_DEFAULT_WAIT_NS = 100;  // barrier waits park instead of spinning (1.58 -> 1.41 ms, profiles/r02_attention_wait_hint_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
@@ -604,6 +604,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   // MODE bit 5: P handed to the MMA issuer in 32-key chunks (own full / empty barrier each) instead of 64-key halves: the chunk a warp
   // writes first was multiplied while it exponentiated its second chunk of the previous tile, so it never waits for the P V MMA
   constexpr bool PCH = (MODE & 32) != 0;
+  constexpr bool LATE = (MODE & 64) != 0;   // MODE bit 6: wait for the free P buffer only before the first tcgen05.st, not before the first exponential
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * (2 * FA_BM);
   const int h = blockIdx.y, b = blockIdx.z;
@@ -752,7 +753,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&s_empty[g]); }
             else mbar_arrive(&s_empty[g]);
           }
-          if (!PCH && c0 == 0) {
+          if (!PCH && !LATE && c0 == 0) {
             mbar_wait_sleep(&p_empty[pb], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // the P V MMAs of tile j-1 have finished reading this half of P
             tc_fence_after();
           }
@@ -768,6 +769,9 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
             else pt_chunk32<POLY, MODE, false>(sr + 32 * t, C, kb, p.n_keys, pk, l);
             if (PCH) {
               mbar_wait_sleep(&p_empty[pb + ((c0 + 32 * t) >> 5)], (uint32_t)((j & 1) ^ 1), p.wait_ns);
+              tc_fence_after();
+            } else if (LATE && c0 == 0 && t == 0) {   // the first 32 exponentials ran while the P V MMAs of tile j-1 were still reading P
+              mbar_wait_sleep(&p_empty[pb], (uint32_t)((j & 1) ^ 1), p.wait_ns);
               tc_fence_after();
             }
             tmem_st16(p_col + (uint32_t)((c0 + 32 * t) >> 1), pk);
@@ -1181,6 +1185,18 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 57: PT_LAUNCH(0, 2, false, 15); break;
     case 58: PT_LAUNCH(8, 2, false, 25); break;  // warp arrivals + both 32-score chunks preloaded
     case 59: PT_LAUNCH(8, 2, false, 17); break;  // preload only
+    case 64: PT_LAUNCH(4, 2, false, 17); break;  // preload, other polynomial shares
+    case 65: PT_LAUNCH(6, 2, false, 17); break;
+    case 66: PT_LAUNCH(0, 2, false, 17); break;
+    case 67: PT_LAUNCH(12, 2, false, 17); break;
+    case 68: PT_LAUNCH(3, 2, false, 17); break;
+    case 69: PT_LAUNCH(0, 2, false, 19); break;  // bottleneck experiment: preload, no MUFU
+    case 70: PT_LAUNCH(5, 2, false, 17); break;
+    case 71: PT_LAUNCH(8, 2, false, 81); break;  // preload + late P-buffer wait
+    case 72: PT_LAUNCH(4, 2, false, 81); break;
+    case 73: PT_LAUNCH(6, 2, false, 81); break;
+    case 74: PT_LAUNCH(0, 2, false, 81); break;
+    case 75: PT_LAUNCH(8, 2, false, 65); break;  // late wait without preload
     case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
     case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
     case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only

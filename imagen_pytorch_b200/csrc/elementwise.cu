@@ -725,6 +725,61 @@ __global__ void __launch_bounds__(256) im2col_init_kernel(const float* __restric
   }
 }
 
+// Same gather with the source window staged in shared memory (image width a multiple of 32): a block's 32 patch rows are 32 consecutive
+// pixels of ONE image row, so everything they read is a ks x (32 + ks - 1) x Cin window.  It is staged channel-innermost, which makes
+// the (dx, c) run of a patch row contiguous; lane i reads 8 consecutive k, i.e. a stride-8 pattern, made conflict-free by the
+// a + (a >> 5) skew.  The direct kernel above needs one L1 wavefront per gathered element (each lane hits a different channel plane
+// or row): 46 M wavefronts = 112 us for the 15x15x3 stem.
+__global__ void __launch_bounds__(256) im2col_init_staged_kernel(const float* __restrict__ img0, int C0, const float* __restrict__ img1, int C1,
+                                                                 const float* __restrict__ img2, int C2, const float* __restrict__ img3, int C3, int B,
+                                                                 int H, int W, int ks, __nv_bfloat16* __restrict__ out, int Kpad) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ int lut[];                             // [Kpad] window offset of k (or -1), then the skewed window
+  const int Cin = C0 + C1 + C2 + C3, pad = ks / 2, K = ks * ks * Cin;
+  const int RW = IM2COL_ROWS + ks - 1;                     // window width in pixels
+  float* win = reinterpret_cast<float*>(lut + Kpad);
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < K) {
+      const int tap = k / Cin, c = k - tap * Cin;
+      v = ((tap / ks) * RW + tap % ks) * Cin + c;
+    }
+    lut[k] = v;
+  }
+  const long long row_begin = (long long)blockIdx.x * IM2COL_ROWS;
+  const int w0 = (int)(row_begin % W), h = (int)((row_begin / W) % H), b = (int)(row_begin / ((long long)W * H));
+  const int nwin = ks * RW * Cin;
+  for (int i = threadIdx.x; i < nwin; i += blockDim.x) {   // i = (c, dy, col): consecutive threads read consecutive image columns
+    const int col = i % RW, dy = (i / RW) % ks, c = i / (RW * ks);
+    const int hh = h + dy - pad, ww = w0 + col - pad;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+      v = c < C0 ? __ldg(img0 + (((long long)b * C0 + c) * H + hh) * W + ww)
+          : c < C0 + C1 ? __ldg(img1 + (((long long)b * C1 + (c - C0)) * H + hh) * W + ww)
+          : c < C0 + C1 + C2 ? __ldg(img2 + (((long long)b * C2 + (c - C0 - C1)) * H + hh) * W + ww)
+                             : __ldg(img3 + (((long long)b * C3 + (c - C0 - C1 - C2)) * H + hh) * W + ww);
+    }
+    const int a = (dy * RW + col) * Cin + c;
+    win[a + (a >> 5)] = v;
+  }
+  __syncthreads();
+  const int vecs = Kpad >> 3;
+  const int nvec = IM2COL_ROWS * vecs;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const int kv = i % vecs, pix = i / vecs;
+    const int k0 = kv << 3, base = pix * Cin;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = lut[k0 + j];
+      const int a = base + e;
+      f[j] = e >= 0 ? win[a + (a >> 5)] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + (row_begin + pix) * Kpad + k0) = pack8(f);
+  }
+}
+
 __global__ void pixel_unshuffle_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int B, int H, int W, int C,
                                        __nv_bfloat16* __restrict__ out) {
   pdl_trigger();
@@ -952,6 +1007,15 @@ extern "C" int b200_im2col_init4(const float* img0, int C0, const float* img1, i
   B200_REQUIRE(img0 && out && C0 > 0 && (C1 == 0 || img1) && (C2 == 0 || img2) && (C3 == 0 || img3), "im2col: null pointer");
   B200_REQUIRE((Kpad & 63) == 0 && Kpad >= ksize * ksize * (C0 + C1 + C2 + C3), "im2col: Kpad=%d too small or not a multiple of 64", Kpad);
   B200_REQUIRE(Kpad * 4 <= 48 * 1024 && C0 + C1 + C2 + C3 < 256, "im2col: patch too large");
+  const int Cin = C0 + C1 + C2 + C3;
+  const int nwin = ksize * (IM2COL_ROWS + ksize - 1) * Cin;
+  const size_t staged_smem = (size_t)Kpad * sizeof(int) + (size_t)(nwin + (nwin >> 5) + 1) * sizeof(float);
+  static const bool staged_on = [] { const char* e = getenv("B200_IMAGEN_IM2COL_STAGED"); return !e || atoi(e) != 0; }();
+  if (staged_on && W % IM2COL_ROWS == 0 && staged_smem <= 160 * 1024) {
+    if (staged_smem > 48 * 1024) B200_SMEM_OPT_IN(im2col_init_staged_kernel, 160 * 1024);
+    B200_CUDA_OK(b200_launch(im2col_init_staged_kernel, dim3((unsigned)((long long)B * H * W / IM2COL_ROWS)), dim3(256), staged_smem, st, img0, C0, img1, C1, img2, C2, img3, C3, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad));
+    return B200_OK;
+  }
   B200_CUDA_OK(b200_launch(im2col_init_kernel, dim3((unsigned)ceil_div64((long long)B * H * W, IM2COL_ROWS)), dim3(256), Kpad * sizeof(int), st, img0, C0, img1, C1, img2, C2, img3, C3, B, H, W, ksize, reinterpret_cast<__nv_bfloat16*>(out), Kpad));
   return B200_OK;
 }

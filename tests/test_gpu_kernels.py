@@ -567,6 +567,24 @@ def test_layout_gathers():
     assert torch.equal(o3[:, :3], img0.permute(0, 2, 3, 1).reshape(-1, 3).to(BF16)) and o3[:, 3:].abs().max() == 0
 
 
+@pytest.mark.parametrize('W,ks,chans', [(32, 15, (3,)), (64, 15, (3, 3)), (64, 7, (3, 3, 3, 3)), (96, 3, (5, 3))])
+def test_im2col_staged_window(W, ks, chans):
+    """Stem patch gather through the shared-memory window (image width a multiple of 32): exact against F.unfold, 1-4 sources."""
+    B, H = 3, 20
+    imgs = [rnd(B, c, H, W, seed=i) for i, c in enumerate(chans)]
+    Cin = sum(chans)
+    Kpad = ops.ceil_to(ks * ks * Cin, 64)
+    out = torch.full((B * H * W, Kpad), 7.0, dtype=BF16, device=DEV)
+    ptrs = []
+    for i in range(4):
+        ptrs += [imgs[i].data_ptr(), chans[i]] if i < len(imgs) else [None, 0]
+    _lib.call('b200_im2col_init4', *ptrs, B, H, W, ks, out.data_ptr(), Kpad, stream())
+    x = torch.cat(imgs, dim=1)
+    cols = F.unfold(x, ks, padding=ks // 2).view(B, Cin, ks * ks, H * W).permute(0, 3, 2, 1).reshape(B * H * W, ks * ks * Cin)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :ks * ks * Cin], cols.to(BF16)) and out[:, ks * ks * Cin:].abs().max() == 0
+
+
 def test_time_conditioning_plumbing():
     R, D, S = 4, 96, 5
     table, th = rnd(S, D), rnd(R, D, seed=1)
