@@ -742,8 +742,15 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < CH; ++i) sr[i] = __float_as_uint(-1.f - (float)(lane + i));
           } else {
+            if (CH == 64 && (MODE & 128)) {          // MODE bit 7: one x64 load instead of two x32 loads in flight
+              tmem_ld64_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0), sr);
+            } else {
 #pragma unroll
-            for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
+              for (int c = 0; c < CH; c += 32) {
+                tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
+                if ((MODE & 256) && c + 32 < CH) tmem_ld_wait();   // MODE bit 8: one load in flight at a time
+              }
+            }
             tmem_ld_wait();
           }
 #pragma unroll
@@ -1197,6 +1204,11 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 73: PT_LAUNCH(6, 2, false, 81); break;
     case 74: PT_LAUNCH(0, 2, false, 81); break;
     case 75: PT_LAUNCH(8, 2, false, 65); break;  // late wait without preload
+    case 76: PT_LAUNCH(6, 2, false, 21); break;  // bottleneck experiment: preload, no TMEM reads
+    case 77: PT_LAUNCH(0, 2, false, 23); break;  // bottleneck experiment: preload, neither MUFU nor TMEM reads
+    case 78: PT_LAUNCH(6, 2, false, 145); break; // preload with one x64 tcgen05.ld
+    case 79: PT_LAUNCH(6, 2, false, 273); break; // preload, the two x32 loads one after the other
+    case 80: PT_LAUNCH(6, 2, false, 209); break; // x64 + late P-buffer wait
     case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
     case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
     case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only
