@@ -19,6 +19,7 @@
 //
 // Replaces the same reference arithmetic as attention.cu (Attention.forward / CrossAttention.forward einsum ->
 // softmax -> einsum, imagen_pytorch.py:565-588, :818-833).
+#include <cstdio>
 #include "ptx.cuh"
 #include <stdlib.h>
 
@@ -63,6 +64,8 @@ struct FaParams {
   int q_heads_first, kv_heads_first;   // coordinate order of the (rows, heads) dims in the tensor maps
   float max_logit;
   uint32_t wait_ns;                    // suspend-time hint of the barrier waits (0 = plain spin); B200_IMAGEN_FA_WAIT_NS
+  long long* trace;                    // development only (MODE bit 9, B200_IMAGEN_FA_TRACE): clock64 stamps of one CTA, [warp][key tile][8]
+  int trace_cta;
 };
 
 template <int NW, bool PF, bool WA>
@@ -604,7 +607,13 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   // MODE bit 5: P handed to the MMA issuer in 32-key chunks (own full / empty barrier each) instead of 64-key halves: the chunk a warp
   // writes first was multiplied while it exponentiated its second chunk of the previous tile, so it never waits for the P V MMA
   constexpr bool PCH = (MODE & 32) != 0;
-  constexpr bool LATE = (MODE & 64) != 0;   // MODE bit 6: wait for the free P buffer only before the first tcgen05.st, not before the first exponential
+  constexpr bool LATE = (MODE & 64) != 0;
+  constexpr bool TRACE = (MODE & 512) != 0;
+  const bool traced = TRACE && p.trace != nullptr && (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == p.trace_cta && (threadIdx.x & 31) == 0;
+#define FA_TR(j_, slot_)                                                                                   \
+  do {                                                                                                     \
+    if (TRACE && traced && (j_) < 64) p.trace[(((threadIdx.x >> 5) * 64 + (j_)) << 3) + (slot_)] = clock64(); \
+  } while (0)   // MODE bit 6: wait for the free P buffer only before the first tcgen05.st, not before the first exponential
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * (2 * FA_BM);
   const int h = blockIdx.y, b = blockIdx.z;
@@ -645,7 +654,9 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % PT_STAGES;
         const uint32_t n = (uint32_t)(j / PT_STAGES);
+        FA_TR(j, 0);
         mbar_wait_sleep(&kv_empty[st], (n & 1u) ^ 1u, p.wait_ns);
+        FA_TR(j, 1);
         mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
         uint8_t* dst = sKV + st * FA_KV_BYTES;
         if (p.kv_heads_first) {
@@ -666,8 +677,11 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
       auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
         const int st = j % PT_STAGES;
+        FA_TR(j, 0);
         mbar_wait_sleep(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1), p.wait_ns);
+        FA_TR(j, 1);
         mbar_wait_sleep(&s_empty[g], (uint32_t)((j & 1) ^ 1), p.wait_ns);
+        FA_TR(j, 2);
         tc_fence_after();
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
 #pragma unroll
@@ -687,6 +701,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           if (hf == 1 && dead1 && j == ntiles - 1) continue;
           const int pb = 4 * g + 2 * hf + ci;
           mbar_wait_sleep(&p_full[pb], (uint32_t)(j & 1), p.wait_ns);
+          FA_TR(j, 3 + u);
           tc_fence_after();
 #pragma unroll
           for (int k = (PCH ? 2 * ci : 0); k < (PCH ? 2 * ci + 2 : 4); ++k) {
@@ -698,6 +713,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           umma_commit(&p_empty[pb]);
         }
         umma_commit(&kv_empty[st]);             // one of the two arrivals that free K_j / V_j
+        FA_TR(j, 7);
       }
       umma_commit(&o_full[g]);
     }
@@ -725,7 +741,9 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         }
         break;
       }
+      FA_TR(j, 0);
       mbar_wait_sleep(&s_full[g], (uint32_t)(j & 1), p.wait_ns);
+      FA_TR(j, 1);
       tc_fence_after();
       bool have_token = !ORDER;
       constexpr int CH = (SUB == 2 && !(MODE & 16)) ? 32 : 64;   // MODE bit 4: all 64 scores of the thread in registers before the first exponential (S freed earlier)
@@ -755,14 +773,17 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           }
 #pragma unroll
           for (int i = 0; i < CH; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
+          FA_TR(j, 2);
           if (c0 + CH == 64 && (SUB == 2 || hh == 1 || last_dead)) {
             tc_fence_before();                  // this thread's share of S_g is in registers
             if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&s_empty[g]); }
             else mbar_arrive(&s_empty[g]);
           }
           if (!PCH && !LATE && c0 == 0) {
+            FA_TR(j, 3);
             mbar_wait_sleep(&p_empty[pb], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // the P V MMAs of tile j-1 have finished reading this half of P
             tc_fence_after();
+            FA_TR(j, 4);
           }
           if (!have_token) {                    // scores are in registers: now wait for this group's turn on the MUFU pipe
             mbar_wait_sleep(&order_bar[g], tok_par, p.wait_ns);
@@ -794,12 +815,14 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&order_bar[g ^ 1]);
         }
+        FA_TR(j, 5);
         if (!PCH) {
           tmem_st_wait();                        // the stores have landed in tensor memory ...
           tc_fence_before();                     // ... and are ordered before the issuer's MMAs through the barrier
           if (WARP_ARRIVE) { __syncwarp(); if (lane == 0) mbar_arrive(&p_full[pb]); }
           else mbar_arrive(&p_full[pb]);
         }
+        FA_TR(j, 6);
       }
     }
     // ---- O / l -> global (with SUB == 2 the two column-half threads of a row add their sums and each stores 32 channels)
@@ -1129,6 +1152,18 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     static const uint32_t wns = [] { const char* ev = getenv("B200_IMAGEN_FA_WAIT_NS"); return (uint32_t)(ev ? atoi(ev) : FA_DEFAULT_WAIT_NS); }();
     p.wait_ns = wns;
   }
+  p.trace = nullptr;
+  p.trace_cta = 0;
+  static const char* trace_path = getenv("B200_IMAGEN_FA_TRACE");   // development: dump one CTA's barrier time line of the next launch(es)
+  static long long* trace_dev = nullptr;
+  constexpr size_t TRACE_WORDS = 20 * 64 * 8;
+  if (trace_path) {
+    if (!trace_dev) B200_CUDA_OK(cudaMalloc(&trace_dev, TRACE_WORDS * sizeof(long long)));
+    B200_CUDA_OK(cudaMemsetAsync(trace_dev, 0, TRACE_WORDS * sizeof(long long), st));
+    p.trace = trace_dev;
+    const char* c = getenv("B200_IMAGEN_FA_TRACE_CTA");
+    p.trace_cta = c ? atoi(c) : 1000;
+  }
   dim3 grid((rows + FA_BM - 1) / FA_BM, n_heads, B);
   // kernel variant: (softmax warps, S prefetch, warp-level barrier arrive).  Default chosen from B200 measurements
   // (profiles/); B200_IMAGEN_FA_VARIANT overrides it for the tuning sweep in tools/sweep_attention.py.
@@ -1209,6 +1244,14 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 78: PT_LAUNCH(6, 2, false, 145); break; // preload with one x64 tcgen05.ld
     case 79: PT_LAUNCH(6, 2, false, 273); break; // preload, the two x32 loads one after the other
     case 80: PT_LAUNCH(6, 2, false, 209); break; // x64 + late P-buffer wait
+    case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;   // default + time-line trace
+    case 82: PT_LAUNCH(6, 2, true, 17); break;   // preload + MUFU token: the two query-tile groups exponentiate in turns
+    case 83: PT_LAUNCH(8, 2, true, 17); break;
+    case 84: PT_LAUNCH(0, 2, true, 17); break;
+    case 85: PT_LAUNCH(4, 2, true, 17); break;
+    case 86: PT_LAUNCH(6, 2, true, 17 + 64); break;
+    case 87: PT_LAUNCH(6, 2, true, 17 + 512); break;   // ... + time-line trace
+    case 88: PT_LAUNCH(3, 2, true, 17); break;
     case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
     case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
     case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only
@@ -1222,5 +1265,14 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   }
 #undef FA_LAUNCH
   B200_LAUNCH_OK();
+  if (trace_path && p.trace) {
+    static long long host[TRACE_WORDS];
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    B200_CUDA_OK(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(host, sizeof(long long), TRACE_WORDS, f);
+      fclose(f);
+    }
+  }
   return B200_OK;
 }
