@@ -309,8 +309,14 @@ def main():
     te_dev = te_host.to(device)
     out_host = torch.empty(args.bs, 3, out_px, out_px).pin_memory()
 
+    own_events = []                                             # (before, after) this rank's own sampling work, all-gather excluded
+
     def step_resident():
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
         img = imagen.sample(text_embeds=te_dev, use_tqdm=False, **skw)
+        eb.record()
+        own_events.append((ea, eb))
         if world > 1:
             img = all_gather_images(img, [args.bs] * world)
         return img
@@ -345,9 +351,15 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    own_events.clear()
     with ClockSampler(local) as clk:
         ms, ms_ranks = timed(step_resident, args.steps)
     clocks = clk.summary()
+    own_ms = [sum(a.elapsed_time(b) for a, b in own_events) / args.steps]   # this rank's shard alone: a slow GPU shows up by index
+    if world > 1:
+        own_all = torch.empty(world, device=device)
+        dist.all_gather_into_tensor(own_all, torch.tensor(own_ms, device=device))
+        own_ms = own_all.tolist()
     launches = imagen.last_launch_count * args.steps
     step_e2e()
     ms_e2e, ms_e2e_ranks = timed(step_e2e, args.steps)
@@ -367,6 +379,7 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': te_host.numel() * 4, 'd2h_bytes_per_step': out_host.numel() * 4},
         'per_rank': {'ms_per_step': [m / args.steps for m in ms_ranks], 'ms_per_step_min': min(ms_ranks) / args.steps,
                      'ms_per_step_median': statistics.median(ms_ranks) / args.steps, 'ms_per_step_max': max(ms_ranks) / args.steps,
+                     'own_sampling_ms_per_step': own_ms,
                      'e2e_ms_per_step': [m / args.steps for m in ms_e2e_ranks],
                      'sm_mhz': [c.get('sm_mhz') for c in rank_clocks], 'reasons': [c.get('reasons') for c in rank_clocks]},
     }

@@ -865,6 +865,244 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// PERSISTENT form of the kernel above (its measured default configuration: 16 softmax warps, scores preloaded, P = exp2(S), P in
+// tensor memory).  tools/attn_keys_scan.py: a CTA of the one-shot kernel costs 5.4 us of launch / prologue / pipeline ramp / epilogue
+// plus 1.15 us per key tile -- 12 % of the 64x64-level launch (33 tiles), 35 % of the 32x32-level one (9 tiles).  Here one CTA per SM
+// walks the work items (256 query rows of one head of one sample) it_0 = blockIdx.x, it_0 + gridDim.x, ...: barriers, tensor memory
+// and tensor-map prefetch are set up once, the K/V ring keeps streaming across item boundaries (the producer runs up to PT_STAGES
+// tiles ahead, i.e. into the next item), the next item's Q tiles are fetched as soon as the last S MMA of the current item has read
+// them, and S(0) of the next item is computed while the softmax warps still scale and store O of the current one.
+// All barrier parities are derived from running counters (key tiles / handed-over P halves / items processed by THIS CTA).
+// ------------------------------------------------------------------------------------------------------------------
+struct FaPersist {
+  int pairs_per_head;      // ceil(rows / 256)
+  int n_heads;
+  long long total_items;   // B * n_heads * pairs_per_head
+};
+
+template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results)
+__global__ void __launch_bounds__(640, 1)
+flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p, const __grid_constant__ FaPersist pp) {
+  pdl_trigger();
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [2] query tiles
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [PT_STAGES] {K, V}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + PT_STAGES * FA_KV_BYTES);
+  uint64_t* q_full = bars;                              // [1]
+  uint64_t* q_empty = bars + 1;                         // [1] (count 2: the last S MMA of both groups)
+  uint64_t* kv_full = bars + 2;                         // [PT_STAGES]
+  uint64_t* kv_empty = kv_full + PT_STAGES;             // [PT_STAGES] (count 2: both groups' P V MMAs)
+  uint64_t* s_full = kv_empty + PT_STAGES;              // [group]
+  uint64_t* s_empty = s_full + 2;                       // [group] (count 256)
+  uint64_t* p_full = s_empty + 2;                       // [group][half] (count 128)
+  uint64_t* p_empty = p_full + 4;                       // [group][half]
+  uint64_t* o_full = p_empty + 4;                       // [group]
+  uint64_t* o_empty = o_full + 2;                       // [group] (count 8: one arrival per softmax warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* sL = reinterpret_cast<float*>(bars + 64);      // [group][sub][128] partial row sums
+  static_assert(2 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 2 + 1 <= 64, "barrier block is 512 bytes");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
+  const int dead = ((ntiles - 1) * FA_BN + 64 >= p.n_keys) ? 1 : 0;   // the last tile's second 64-key half holds no valid key
+  constexpr uint32_t TM_O = 256, TM_P = 384;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);
+    for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 256);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_empty[g], 8);
+      for (int i = 0; i < 2; ++i) { mbar_init(&p_full[2 * g + i], 128); mbar_init(&p_empty[2 * g + i], 1); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      uint32_t T = 0;                                   // key tiles loaded by this CTA so far
+      int n = 0;
+      for (long long it = blockIdx.x; it < pp.total_items; it += gridDim.x, ++n) {
+        const int pair = (int)(it % pp.pairs_per_head);
+        const int h = (int)((it / pp.pairs_per_head) % pp.n_heads), b = (int)(it / ((long long)pp.pairs_per_head * pp.n_heads));
+        const int row0 = pair * (2 * FA_BM);
+        if (n > 0) mbar_wait_sleep(q_empty, (uint32_t)((n - 1) & 1), p.wait_ns);   // the previous item's last S MMAs have read Q
+        mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
+        for (int g = 0; g < 2; ++g) {
+          if (p.q_heads_first) tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, h, row0 + g * FA_BM, b);
+          else tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, row0 + g * FA_BM, h, b);
+        }
+        for (int j = 0; j < ntiles; ++j, ++T) {
+          const int st = (int)(T % PT_STAGES);
+          mbar_wait_sleep(&kv_empty[st], ((T / PT_STAGES) & 1u) ^ 1u, p.wait_ns);
+          mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
+          uint8_t* dst = sKV + st * FA_KV_BYTES;
+          if (p.kv_heads_first) {
+            tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
+            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+          } else {
+            tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
+            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (lane == 0) {
+      // ---------------- MMA issuer of group g
+      const int g = warp - 1;
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+      uint32_t T0 = 0, H1 = 0;                          // key tiles / second-half P hand-overs before the current item
+      int n = 0;
+      for (long long it = blockIdx.x; it < pp.total_items; it += gridDim.x, ++n, T0 += (uint32_t)ntiles, H1 += (uint32_t)(ntiles - dead)) {
+        auto issue_s = [&](int j) {                     // S_g(j) = Q_g K_j^T once group g has pulled its previous S into registers
+          const uint32_t T = T0 + (uint32_t)j;
+          const int st = (int)(T % PT_STAGES);
+          mbar_wait_sleep(&kv_full[st], (T / PT_STAGES) & 1u, p.wait_ns);
+          mbar_wait_sleep(&s_empty[g], (T & 1u) ^ 1u, p.wait_ns);
+          tc_fence_after();
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
+#pragma unroll
+          for (int k = 0; k < FA_D / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          if (j == ntiles - 1) umma_commit(q_empty);    // Q of this item is no longer needed by this group
+        };
+        mbar_wait_sleep(q_full, (uint32_t)(n & 1), p.wait_ns);
+        issue_s(0);
+        for (int j = 0; j < ntiles; ++j) {
+          if (j + 1 < ntiles) issue_s(j + 1);
+          const uint32_t T = T0 + (uint32_t)j;
+          const int st = (int)(T % PT_STAGES);
+          const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+          for (int hf = 0; hf < 2; ++hf) {              // the first 64 keys are multiplied while the second 64 are exponentiated
+            if (hf == 1 && dead && j == ntiles - 1) break;
+            const int pb = 2 * g + hf;
+            const uint32_t ph = hf == 0 ? T : H1 + (uint32_t)j;
+            mbar_wait_sleep(&p_full[pb], ph & 1u, p.wait_ns);
+            if (j == 0 && hf == 0) mbar_wait_sleep(&o_empty[g], (uint32_t)((n & 1) ^ 1), p.wait_ns);   // the previous item's O has been read
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a_tmem = tmem_base + TM_P + (uint32_t)(g * 64 + hf * 32 + k * 8);
+              const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((hf * 4 + k) * 16 * 128), 1024, 1024);
+              umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, (j | hf | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&p_empty[pb]);
+          }
+          umma_commit(&kv_empty[st]);                   // one of the two arrivals that free K_j / V_j
+        }
+        umma_commit(&o_full[g]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax / epilogue: group g, thread = (query row of that group, 64-key half)
+    const int idx = warp - 4;
+    const int g = idx >> 3;
+    const int sub = (idx >> 2) & 1;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int pb = 2 * g + sub;
+    const uint32_t p_col = tmem_base + lane_off + TM_P + (uint32_t)(g * 64 + sub * 32);
+    float* sLg = sL + g * 2 * FA_BM;
+    uint32_t T0 = 0, H1 = 0;
+    int n = 0;
+    for (long long it = blockIdx.x; it < pp.total_items; it += gridDim.x, ++n, T0 += (uint32_t)ntiles, H1 += (uint32_t)(ntiles - dead)) {
+      const int pair = (int)(it % pp.pairs_per_head);
+      const int h = (int)((it / pp.pairs_per_head) % pp.n_heads), b = (int)(it / ((long long)pp.pairs_per_head * pp.n_heads));
+      const int row0 = pair * (2 * FA_BM);
+      float l = 0.f;
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t T = T0 + (uint32_t)j;
+        const int key0 = j * FA_BN;
+        mbar_wait_sleep(&s_full[g], T & 1u, p.wait_ns);
+        tc_fence_after();
+        if (sub == 1 && dead && j == ntiles - 1) {      // nothing valid in this warp's half of the last tile: only release S
+          tc_fence_before();
+          mbar_arrive(&s_empty[g]);
+          break;
+        }
+        uint32_t sr[64];
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + sub * 64), sr);
+        tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + sub * 64 + 32), sr + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
+        tc_fence_before();
+        mbar_arrive(&s_empty[g]);                       // this thread's share of S_g is in registers
+        const uint32_t ph = sub == 0 ? T : H1 + (uint32_t)j;
+        mbar_wait_sleep(&p_empty[pb], (ph & 1u) ^ 1u, p.wait_ns);   // the P V MMAs of the previous tile have finished reading this half of P
+        tc_fence_after();
+        const bool ragged = key0 + FA_BN > p.n_keys;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint32_t pk[16];
+          const int kb = key0 + sub * 64 + 32 * t;
+          if (ragged) pt_chunk32<POLY, 1 | (MODE & 2), true>(sr + 32 * t, 0.f, kb, p.n_keys, pk, l);
+          else pt_chunk32<POLY, 1 | (MODE & 2), false>(sr + 32 * t, 0.f, kb, p.n_keys, pk, l);
+          tmem_st16(p_col + (uint32_t)(16 * t), pk);
+        }
+        tmem_st_wait();                                 // the stores have landed in tensor memory ...
+        tc_fence_before();                              // ... and are ordered before the issuer's MMAs through the barrier
+        mbar_arrive(&p_full[pb]);
+      }
+      // ---- O / l -> global: the two column-half threads of a row add their sums and each stores 32 channels
+      mbar_wait_sleep(&o_full[g], (uint32_t)(n & 1), p.wait_ns);
+      tc_fence_after();
+      sLg[sub * FA_BM + r] = l;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");         // the 8 softmax warps of this group
+      l = sLg[r] + sLg[FA_BM + r];
+      uint32_t orr[32];
+      tmem_ld32_nowait(tmem_base + lane_off + TM_O + (uint32_t)(g * FA_D + sub * 32), orr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(orr[i]));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[g]);          // O_g may be overwritten by the next item's first P V MMA
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");         // sLg is rewritten by the next item only after everybody has read it
+      const float inv = 1.f / l;
+      const int row = row0 + g * FA_BM + r;
+      if (row < p.rows) {
+        __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + sub * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 8 * t) = u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Few-keys (cross-) attention on tcgen05: <= 64 keys per head (the 39 context rows of CrossAttention).  The work is memory bound
 // (q in, o out: 268 MB at the 64x64 level), so the kernel is PERSISTENT: one CTA per SM walks a contiguous range of work items
 // (sample b, 128-row query tile, head h); the K and V rows of all heads of the current sample stay resident in shared memory
@@ -1252,6 +1490,22 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 86: PT_LAUNCH(6, 2, true, 17 + 64); break;
     case 87: PT_LAUNCH(6, 2, true, 17 + 512); break;   // ... + time-line trace
     case 88: PT_LAUNCH(3, 2, true, 17); break;
+#define PTP_LAUNCH(POLY, MODE)                                                                                                   \
+  {                                                                                                                                \
+    B200_SMEM_OPT_IN((flash_attn_ptp_kernel<POLY, MODE>), PT_SMEM);                                                                \
+    FaPersist pp;                                                                                                                  \
+    pp.pairs_per_head = (rows + 2 * FA_BM - 1) / (2 * FA_BM);                                                                      \
+    pp.n_heads = n_heads;                                                                                                          \
+    pp.total_items = (long long)B * n_heads * pp.pairs_per_head;                                                                   \
+    const long long ctas = pp.total_items < (long long)sm_count() ? pp.total_items : (long long)sm_count();                         \
+    B200_CUDA_OK(b200_launch(flash_attn_ptp_kernel<POLY, MODE>, dim3((unsigned)ctas), dim3(640), PT_SMEM, st, mq, mk, mv, p, pp));  \
+  }
+    case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs, otherwise variant 65
+    case 91: PTP_LAUNCH(8, 0); break;
+    case 92: PTP_LAUNCH(4, 0); break;
+    case 93: PTP_LAUNCH(0, 0); break;
+    case 94: PTP_LAUNCH(0, 2); break;            // bottleneck experiment: persistent, no MUFU
+#undef PTP_LAUNCH
     case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
     case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
     case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only

@@ -17,7 +17,7 @@ for N in ${SCALE_NS:-1 8 2 4}; do
 import json,sys
 for l in sys.stdin:
     d=json.loads(l); pr=d['per_rank']
-    print('  value %.3f images/s  ms/step %.1f  e2e %.3f  per-rank ms min/med/max %.1f/%.1f/%.1f  sm_mhz %s  reasons %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], pr['ms_per_step_min'], pr['ms_per_step_median'], pr['ms_per_step_max'], pr['sm_mhz'], pr['reasons']))
+    print('  value %.3f images/s  ms/step %.1f  e2e %.3f  own sampling ms per rank %s  sm_mhz %s  reasons %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], ['%.1f' % x for x in pr.get('own_sampling_ms_per_step', [])], pr['sm_mhz'], pr['reasons']))
 "
   grep -E "NCCL INFO.*(comm 0x.* rank 0 nranks|Init COMPLETE|NVLS|Connected all)" $OUT/scale_$N.log | head -4
   tail -n 2 $OUT/scale_$N.log | grep -v '^{' | cut -c1-200
