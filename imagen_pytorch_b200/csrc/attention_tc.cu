@@ -2,20 +2,18 @@
 //
 // Cosine-sim attention makes the logits bounded: q and k are unit vectors times learned per-dim scales, so
 // |s| <= 8 * max_d|q_scale_d * k_scale_d| (Cauchy-Schwarz).  With that bound C (in log2 units; Q arrives
-// pre-multiplied by 8*log2e) the softmax needs NO running maximum:  P = exp2(S - C) in (0, 1], so the output
-// accumulator O in TMEM is never rescaled and a key tile costs exactly two MMAs + one exp2 per score.
-// The host only takes this path when C is small enough that 2^(-2C) stays far above fp32 underflow;
-// otherwise the online-softmax kernel in attention.cu is used.
+// pre-multiplied by 8*log2e) the softmax needs NO running maximum and the output accumulator O in TMEM is never rescaled:
+// a key tile costs exactly two MMAs + one exp2 per score.  The host only takes this path when C is small enough that the
+// row sums stay inside fp32; otherwise the online-softmax kernel in attention.cu is used.
 //
-// Per CTA: 128 query rows (= the 128 TMEM lanes) x all keys, in tiles of 128 keys.
-//   warp 0      TMA producer: Q tile once, then a 3-stage ring of {K tile, V tile} (128 keys x 64, 128B swizzle)
-//   warp 1      tcgen05.mma issuer:  S[j%2] = Q K_j^T  (128x128x64, fp32 in TMEM, double buffered) and
-//               O += P_j V_j (128x64x128; A = P_j from shared memory K-major, B = V_j MN-major)
-//   warps 2..17 softmax: thread = (query row, 32-key slice): tcgen05.ld S -> exp2 -> bf16 P written to shared memory in the
-//               128B-swizzled K-major layout the MMA reads (fence.proxy.async), row sums in registers;
-//               at the end O / l -> bf16 -> global.
-// S of tile j+1 is issued before the P V MMA of tile j, so the tensor pipe works on the next scores while the
-// softmax warps are busy with the current ones.
+// Kernels in this file (history and measurements: DESIGN.md section 3, profiles/r0*_attention_*):
+//   flash_attn_pp_kernel   ping-pong over two 128-row query tiles, P through shared memory (round-1 default, kept as variant 12)
+//   flash_attn_pt_kernel   + P in tensor memory (tcgen05.st, TS-form MMA), scores preloaded so that S is released before the first
+//                          exponential: the default for long key sequences (variant 65)
+//   flash_attn_ptp_kernel  the same pipeline as persistent CTAs: the default for <= FA_PERSISTENT_MAX_TILES key tiles
+//   cross_attn_tc_kernel   <= 64 keys (cross-attention over the text tokens), persistent, K/V of all heads resident
+// Every kernel: warp 0 TMA producer (Q tiles, K/V ring, 128-byte swizzle), one MMA-issuer thread per query tile, softmax warps
+// that own (query row, key slice) and read S / write P / read O with tcgen05.ld / tcgen05.st.
 //
 // Replaces the same reference arithmetic as attention.cu (Attention.forward / CrossAttention.forward einsum ->
 // softmax -> einsum, imagen_pytorch.py:565-588, :818-833).
@@ -28,15 +26,12 @@ namespace {
 constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
-constexpr int FA_STAGES = 3;
-constexpr int FA_DEFAULT_VARIANT = 65;   // ping-pong, P in tensor memory, 16 softmax warps, all 64 scores of a thread preloaded (S freed at once), P = exp2(S), 1/6 of the exp2 on the FMA pipe
+constexpr int FA_PERSISTENT_MAX_TILES = 17;  // persistent kernel up to 2176 keys: 13.7 vs 15.5 us per CTA item at 9 tiles, 44.2 vs 43.4 at 33 (profiles/r02_attention_persistent_sweep.txt)
 constexpr int FA_DEFAULT_WAIT_NS = 100;  // barrier waits park instead of spinning (1.58 -> 1.41 ms, profiles/r02_attention_wait_hint_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
 constexpr int FA_KV_BYTES = 2 * FA_K_BYTES;         // K + V per stage
-constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;       // 32 KB (two 64-key K-major blocks)
 constexpr int FA_TMEM_COLS = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
-constexpr int FA_SMEM = FA_Q_BYTES + FA_STAGES * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256 + 2048;   // + row-sum exchange
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -68,250 +63,12 @@ struct FaParams {
   int trace_cta;
 };
 
-template <int NW, bool PF, bool WA>
-__global__ void __launch_bounds__(64 + 32 * NW, 1)
-flash_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
-  extern __shared__ uint8_t fa_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + FA_Q_BYTES;
-  uint8_t* sP = sKV + FA_STAGES * FA_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
-  uint64_t* q_full = bars;                       // [1]
-  uint64_t* kv_full = bars + 1;                  // [STAGES]
-  uint64_t* kv_empty = kv_full + FA_STAGES;      // [STAGES]
-  uint64_t* s_full = kv_empty + FA_STAGES;       // [2]
-  uint64_t* s_empty = s_full + 2;                // [2]
-  uint64_t* p_full = s_empty + 2;                // [2]
-  uint64_t* p_empty = p_full + 2;                // [2]
-  uint64_t* o_full = p_empty + 2;                // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* sL = reinterpret_cast<float*>(bars + 32);   // [4][128] partial row sums of the four 32-key column slices
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * FA_BM;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < FA_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], WA ? NW : 32 * NW);   // softmax threads (or one lane per warp) arrive after their tcgen05.ld of the buffer
-      mbar_init(&p_full[s], WA ? NW : 32 * NW);    // ... and after writing their slice of the P row
-      mbar_init(&p_empty[s], 1);
-    }
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer
-      mbar_expect_tx(q_full, FA_Q_BYTES);
-      if (p.q_heads_first) tma_load_4d(sQ, &mapQ, q_full, 0, h, row0, b);
-      else tma_load_4d(sQ, &mapQ, q_full, 0, row0, h, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % FA_STAGES;
-        const uint32_t n = (uint32_t)(j / FA_STAGES);
-        mbar_wait(&kv_empty[st], (n & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
-        uint8_t* dst = sKV + st * FA_KV_BYTES;
-        if (p.kv_heads_first) {
-          tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
-          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
-        } else {
-          tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
-          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      // S: M=128, N=128, A/B K-major.   PV: M=128, N=64, A K-major, B MN-major (bit 16).
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t tmem_o = tmem_base + 256;
-      auto issue_s = [&](int j) {
-        const int st = j % FA_STAGES, buf = j & 1;
-        mbar_wait(&kv_full[st], (uint32_t)((j / FA_STAGES) & 1));
-        mbar_wait(&s_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));   // softmax finished reading S[buf] (tile j-2)
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + st * FA_KV_BYTES);
-        const uint64_t adesc = make_sw128_kmajor_desc(q_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(k_addr);
-#pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(buf * FA_BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[buf]);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_s(j + 1);
-        const int st = j % FA_STAGES, buf = j & 1;
-        mbar_wait(&p_full[buf], (uint32_t)((j >> 1) & 1));         // softmax wrote P_j (and fenced it to the async proxy)
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + buf * FA_P_BYTES);
-        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
-#pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) {
-          // A: P block (k/4) of 64 keys, 32 B per 16-key step inside the swizzled row; B: 16 key rows of V = 2 KB
-          const uint64_t adesc = make_sw128_kmajor_desc(p_addr + (uint32_t)((k >> 2) * (FA_BM * 128) + (k & 3) * 32));
-          const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)(k * 16 * 128), 1024, 1024);
-          umma_bf16(tmem_o, adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&kv_empty[st]);   // K_j (read by the S MMA issued earlier) and V_j are free
-        umma_commit(&p_empty[buf]);
-      }
-      umma_commit(o_full);
-    }
-  } else {
-    // ---------------- softmax / epilogue warps: thread = (query row, CPT-key slice of every key tile), NW/4 warps per
-    // scheduler sub-partition.  With PF the TMEM read of tile j+1 is in flight while tile j is exponentiated.
-    constexpr int NSL = NW / 4;             // column slices
-    constexpr int CPT = FA_BN / NSL;        // key columns per thread per tile: 128 / 64 / 32
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int slice = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    float l = 0.f;
-    const float C = p.max_logit;
-    uint32_t cur[CPT];
-    uint32_t nxt[PF ? CPT : 1];
-    auto arrive = [&](uint64_t* bar) {
-      if (WA) { __syncwarp(); if (lane == 0) mbar_arrive(bar); }
-      else mbar_arrive(bar);
-    };
-    auto load_s = [&](int buf, uint32_t* dst) {
-#pragma unroll
-      for (int c = 0; c < CPT; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(buf * FA_BN + slice * CPT + c), dst + c);
-    };
-    if (PF) {
-      mbar_wait(&s_full[0], 0);
-      tc_fence_after();
-      load_s(0, cur);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(cur[i]));   // pin the destination registers behind the wait
-      tc_fence_before();
-      arrive(&s_empty[0]);
-    }
-    for (int j = 0; j < ntiles; ++j) {
-      const int buf = j & 1;
-      const uint32_t par = (uint32_t)((j >> 1) & 1);
-      const bool more = j + 1 < ntiles;
-      if (PF) {
-        if (more) {                             // start reading S_{j+1} (issued by the MMA warp one tile ahead)
-          const int nb = (j + 1) & 1;
-          mbar_wait(&s_full[nb], (uint32_t)(((j + 1) >> 1) & 1));
-          tc_fence_after();
-          load_s(nb, nxt);
-        }
-        mbar_wait(&p_empty[buf], par ^ 1u);     // the P V MMA that read P[buf] two tiles ago has finished
-      } else {
-        mbar_wait(&s_full[buf], par);
-        tc_fence_after();
-        load_s(buf, cur);
-        mbar_wait(&p_empty[buf], par ^ 1u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(cur[i]));
-        tc_fence_before();
-        arrive(&s_empty[buf]);                  // S[buf] is in registers: the tensor pipe may overwrite it with tile j+2
-      }
-      const int key0 = j * FA_BN + slice * CPT;
-      const bool ragged = key0 + CPT > p.n_keys;
-      // this thread's CPT*2 bytes of the P row: 16-byte chunks of the 64-key blocks, XOR-swizzled by the row
-      uint8_t* prow = sP + buf * FA_P_BYTES + r * 128;
-#pragma unroll
-      for (int t = 0; t < CPT / 8; ++t) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          float p0 = ex2_approx(__uint_as_float(cur[8 * t + i]) - C);
-          float p1 = ex2_approx(__uint_as_float(cur[8 * t + i + 1]) - C);
-          if (ragged) {
-            if (key0 + 8 * t + i >= p.n_keys) p0 = 0.f;
-            if (key0 + 8 * t + i + 1 >= p.n_keys) p1 = 0.f;
-          }
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        const int col = slice * CPT + 8 * t;    // first key column of this 16-byte chunk within the tile
-        *reinterpret_cast<uint4*>(prow + (col >> 6) * (FA_BM * 128) + ((((col & 63) >> 3) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      fence_proxy_async_smem();                 // make the generic-proxy P writes visible to the tensor-core (async) proxy
-      arrive(&p_full[buf]);
-      if (PF && more) {
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) asm volatile("" : "+r"(nxt[i]));
-        tc_fence_before();
-        arrive(&s_empty[(j + 1) & 1]);          // S_{j+1} is in registers: the tensor pipe may overwrite the buffer with tile j+3
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) cur[i] = nxt[i];
-      }
-    }
-    // ---- O / l -> global: each slice stores 64/NSL of the 64 output channels
-    sL[slice * FA_BM + r] = l;
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory");   // softmax warps only
-    float lsum = 0.f;
-#pragma unroll
-    for (int i = 0; i < NSL; ++i) lsum += sL[i * FA_BM + r];
-    const float inv = 1.f / lsum;
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    constexpr int OC = FA_D / NSL;          // 64 / 32 / 16 output channels per thread
-    const int row = row0 + r;
-    __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + slice * OC;
-    uint32_t orr[OC];
-    if (OC == 16) tmem_ld16_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * OC), orr);
-    else {
-#pragma unroll
-      for (int c = 0; c < OC; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(256 + slice * OC + c), orr + c);
-    }
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < OC; ++i) asm volatile("" : "+r"(orr[i]));
-    if (row < p.rows) {
-#pragma unroll
-      for (int t = 0; t < OC / 8; ++t) {
-        uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
-        u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
-        u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
-        u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + 8 * t) = u;
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, FA_TMEM_COLS);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // Ping-pong variant: TWO 128-row query tiles (groups A and B) per CTA share one K/V stream.  Each group has its own
 // MMA issuer thread, S accumulator, double-buffered P, O accumulator and four softmax warps, so the groups are fully
 // decoupled: while one waits on its TMEM read / proxy fence / barrier round trip the other one exponentiates, and the S
 // of the next key tile is issued as soon as a group has pulled its current scores into registers.
-// (Measured on B200: in the one-tile kernel above the softmax warps issue only ~27% of the time regardless of their
+// (Measured on B200: in the round-1 one-tile kernel the softmax warps issue only ~27% of the time regardless of their
 // number -- the per-tile dependency chain, not MUFU, was the limit; a first ping-pong with ONE issuer thread and a
 // single P buffer per group still had the softmax warps waiting on p_empty / the in-order issuer: 1.91 ms.)
 // TMEM: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
@@ -880,7 +637,7 @@ struct FaPersist {
   long long total_items;   // B * n_heads * pairs_per_head
 };
 
-template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results)
+template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results); bit 2 = per-CTA rotated key-tile order
 __global__ void __launch_bounds__(640, 1)
 flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p, const __grid_constant__ FaPersist pp) {
@@ -908,6 +665,10 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
   const int dead = ((ntiles - 1) * FA_BN + 64 >= p.n_keys) ? 1 : 0;   // the last tile's second 64-key half holds no valid key
   constexpr uint32_t TM_O = 256, TM_P = 384;
+  // The sum over key tiles has no running max, so its order is free: every CTA starts at a different tile.  The persistent CTAs start
+  // together and stay in lock step; without the rotation all 148 SMs ask L2 for the same 32 KB K/V tile at the same moment.
+  const int rot = (MODE & 4) ? (int)((blockIdx.x * 5u) % (uint32_t)ntiles) : 0;
+  const int jd = (ntiles - 1 - rot + ntiles) % ntiles;       // loop position of the last (possibly half-dead, possibly ragged) tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapQ);
@@ -952,12 +713,13 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           mbar_wait_sleep(&kv_empty[st], ((T / PT_STAGES) & 1u) ^ 1u, p.wait_ns);
           mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
           uint8_t* dst = sKV + st * FA_KV_BYTES;
+          const int jt = j + rot < ntiles ? j + rot : j + rot - ntiles;
           if (p.kv_heads_first) {
-            tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
-            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+            tma_load_4d(dst, &mapK, &kv_full[st], 0, h, jt * FA_BN, b);
+            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, jt * FA_BN, b);
           } else {
-            tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
-            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+            tma_load_4d(dst, &mapK, &kv_full[st], 0, jt * FA_BN, h, b);
+            tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, jt * FA_BN, h, b);
           }
         }
       }
@@ -993,9 +755,9 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           const int st = (int)(T % PT_STAGES);
           const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
           for (int hf = 0; hf < 2; ++hf) {              // the first 64 keys are multiplied while the second 64 are exponentiated
-            if (hf == 1 && dead && j == ntiles - 1) break;
+            if (hf == 1 && dead && j == jd) break;
             const int pb = 2 * g + hf;
-            const uint32_t ph = hf == 0 ? T : H1 + (uint32_t)j;
+            const uint32_t ph = hf == 0 ? T : H1 + (uint32_t)(j - ((dead && j > jd) ? 1 : 0));
             mbar_wait_sleep(&p_full[pb], ph & 1u, p.wait_ns);
             if (j == 0 && hf == 0) mbar_wait_sleep(&o_empty[g], (uint32_t)((n & 1) ^ 1), p.wait_ns);   // the previous item's O has been read
             tc_fence_after();
@@ -1032,13 +794,13 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       float l = 0.f;
       for (int j = 0; j < ntiles; ++j) {
         const uint32_t T = T0 + (uint32_t)j;
-        const int key0 = j * FA_BN;
+        const int key0 = (j + rot < ntiles ? j + rot : j + rot - ntiles) * FA_BN;
         mbar_wait_sleep(&s_full[g], T & 1u, p.wait_ns);
         tc_fence_after();
-        if (sub == 1 && dead && j == ntiles - 1) {      // nothing valid in this warp's half of the last tile: only release S
+        if (sub == 1 && dead && j == jd) {              // nothing valid in this warp's half of the last tile: only release S
           tc_fence_before();
           mbar_arrive(&s_empty[g]);
-          break;
+          continue;
         }
         uint32_t sr[64];
         tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + sub * 64), sr);
@@ -1048,7 +810,7 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         for (int i = 0; i < 64; ++i) asm volatile("" : "+r"(sr[i]));   // pin the destination registers behind the wait
         tc_fence_before();
         mbar_arrive(&s_empty[g]);                       // this thread's share of S_g is in registers
-        const uint32_t ph = sub == 0 ? T : H1 + (uint32_t)j;
+        const uint32_t ph = sub == 0 ? T : H1 + (uint32_t)(j - ((dead && j > jd) ? 1 : 0));
         mbar_wait_sleep(&p_empty[pb], (ph & 1u) ^ 1u, p.wait_ns);   // the P V MMAs of the previous tile have finished reading this half of P
         tc_fence_after();
         const bool ragged = key0 + FA_BN > p.n_keys;
@@ -1402,94 +1164,22 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     const char* c = getenv("B200_IMAGEN_FA_TRACE_CTA");
     p.trace_cta = c ? atoi(c) : 1000;
   }
-  dim3 grid((rows + FA_BM - 1) / FA_BM, n_heads, B);
-  // kernel variant: (softmax warps, S prefetch, warp-level barrier arrive).  Default chosen from B200 measurements
-  // (profiles/); B200_IMAGEN_FA_VARIANT overrides it for the tuning sweep in tools/sweep_attention.py.
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("B200_IMAGEN_FA_VARIANT");
-    variant = e ? atoi(e) : FA_DEFAULT_VARIANT;
-  }
-#define FA_LAUNCH(NW, PF, WA)                                                                                                      \
-  {                                                                                                                                \
-    B200_SMEM_OPT_IN((flash_attn_tc_kernel<NW, PF, WA>), FA_SMEM);                                                                 \
-    flash_attn_tc_kernel<NW, PF, WA><<<grid, 64 + 32 * NW, FA_SMEM, st>>>(mq, mk, mv, p);                                         \
-  }
-  switch (variant) {
-    case 0: FA_LAUNCH(4, false, false); break;
-    case 1: FA_LAUNCH(8, false, false); break;
-    case 2: FA_LAUNCH(8, true, false); break;
-    case 3: FA_LAUNCH(16, false, false); break;
-    case 4: FA_LAUNCH(16, true, false); break;
-    case 5: FA_LAUNCH(8, false, true); break;
-    case 6: FA_LAUNCH(8, true, true); break;
-    case 7: FA_LAUNCH(16, true, true); break;
-    case 8: FA_LAUNCH(4, false, true); break;
+  // Kernel variant: the defaults were chosen from B200 measurements (profiles/r02_attention_*); B200_IMAGEN_FA_VARIANT selects one of
+  // the kept alternatives for tools/sweep_attention.py, B200_IMAGEN_FA_PERSISTENT=0 keeps the one-shot kernel for short key sequences.
+  static const int variant = [] { const char* e = getenv("B200_IMAGEN_FA_VARIANT"); return e ? atoi(e) : -1; }();
+  static const bool persistent_on = [] { const char* e = getenv("B200_IMAGEN_FA_PERSISTENT"); return !e || atoi(e) != 0; }();
+  const int ntiles = (n_keys + FA_BN - 1) / FA_BN;
+  const dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);
 #define PP_LAUNCH(POLY, SUB)                                                                                                     \
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_pp_kernel<POLY, SUB>), PP_SMEM);                                                                  \
-    dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
     B200_CUDA_OK(b200_launch(flash_attn_pp_kernel<POLY, SUB>, grid2, dim3(128 + 256 * SUB), PP_SMEM, st, mq, mk, mv, p));           \
   }
-    case 10: PP_LAUNCH(4, 1); break;   // ping-pong, 1/4 of the exponentials on the FMA pipe
-    case 11: PP_LAUNCH(2, 1); break;   // ping-pong, 1/2
-    case 12: PP_LAUNCH(0, 2); break;   // ping-pong, 16 softmax warps (column halves)
-    case 13: PP_LAUNCH(4, 2); break;   // ... + 1/4 polynomial exp2
 #define PT_LAUNCH(POLY, SUB, ORDER, MODE)                                                                                        \
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_pt_kernel<POLY, SUB, ORDER, MODE>), PT_SMEM);                                                     \
-    dim3 grid2((rows + 2 * FA_BM - 1) / (2 * FA_BM), n_heads, B);                                                                  \
     B200_CUDA_OK(b200_launch(flash_attn_pt_kernel<POLY, SUB, ORDER, MODE>, grid2, dim3(128 + 256 * SUB), PT_SMEM, st, mq, mk, mv, p)); \
   }
-    case 20: PT_LAUNCH(0, 2, false, 0); break;   // P in tensor memory (tcgen05.st + TS MMA), 16 softmax warps
-    case 23: PT_LAUNCH(4, 2, false, 0); break;   // ... + 1/4 of the exponentials on the FMA pipe
-    case 26: PT_LAUNCH(0, 1, false, 0); break;   // P in tensor memory, 8 softmax warps (one full row per thread)
-    case 30: PT_LAUNCH(0, 2, true, 0); break;    // + MUFU token between the two groups (slower: profiles/r02_attention_variant_sweep.txt)
-    case 40: PT_LAUNCH(0, 2, false, 1); break;   // P = exp2(S) without the "- C" (one FADD less per score)
-    case 41: PT_LAUNCH(8, 2, false, 1); break;
-    case 35: PT_LAUNCH(6, 2, false, 1); break;
-    case 38: PT_LAUNCH(12, 2, false, 1); break;
-    case 42: PT_LAUNCH(4, 2, false, 1); break;
-    case 43: PT_LAUNCH(3, 2, false, 1); break;
-    case 46: PT_LAUNCH(0, 1, false, 1); break;
-    case 47: PT_LAUNCH(4, 1, false, 1); break;
-    case 39: PT_LAUNCH(2, 1, false, 1); break;
-    case 48: PT_LAUNCH(3, 1, false, 1); break;
-    case 49: PT_LAUNCH(5, 1, false, 1); break;
-    case 44: PT_LAUNCH(6, 1, false, 1); break;
-    case 45: PT_LAUNCH(8, 1, false, 1); break;
-    case 53: PT_LAUNCH(0, 2, false, 9); break;   // one barrier arrival per warp
-    case 54: PT_LAUNCH(8, 2, false, 9); break;
-    case 55: PT_LAUNCH(4, 2, false, 9); break;
-    case 56: PT_LAUNCH(4, 1, false, 9); break;
-    case 57: PT_LAUNCH(0, 2, false, 15); break;
-    case 58: PT_LAUNCH(8, 2, false, 25); break;  // warp arrivals + both 32-score chunks preloaded
-    case 59: PT_LAUNCH(8, 2, false, 17); break;  // preload only
-    case 64: PT_LAUNCH(4, 2, false, 17); break;  // preload, other polynomial shares
-    case 65: PT_LAUNCH(6, 2, false, 17); break;
-    case 66: PT_LAUNCH(0, 2, false, 17); break;
-    case 67: PT_LAUNCH(12, 2, false, 17); break;
-    case 68: PT_LAUNCH(3, 2, false, 17); break;
-    case 69: PT_LAUNCH(0, 2, false, 19); break;  // bottleneck experiment: preload, no MUFU
-    case 70: PT_LAUNCH(5, 2, false, 17); break;
-    case 71: PT_LAUNCH(8, 2, false, 81); break;  // preload + late P-buffer wait
-    case 72: PT_LAUNCH(4, 2, false, 81); break;
-    case 73: PT_LAUNCH(6, 2, false, 81); break;
-    case 74: PT_LAUNCH(0, 2, false, 81); break;
-    case 75: PT_LAUNCH(8, 2, false, 65); break;  // late wait without preload
-    case 76: PT_LAUNCH(6, 2, false, 21); break;  // bottleneck experiment: preload, no TMEM reads
-    case 77: PT_LAUNCH(0, 2, false, 23); break;  // bottleneck experiment: preload, neither MUFU nor TMEM reads
-    case 78: PT_LAUNCH(6, 2, false, 145); break; // preload with one x64 tcgen05.ld
-    case 79: PT_LAUNCH(6, 2, false, 273); break; // preload, the two x32 loads one after the other
-    case 80: PT_LAUNCH(6, 2, false, 209); break; // x64 + late P-buffer wait
-    case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;   // default + time-line trace
-    case 82: PT_LAUNCH(6, 2, true, 17); break;   // preload + MUFU token: the two query-tile groups exponentiate in turns
-    case 83: PT_LAUNCH(8, 2, true, 17); break;
-    case 84: PT_LAUNCH(0, 2, true, 17); break;
-    case 85: PT_LAUNCH(4, 2, true, 17); break;
-    case 86: PT_LAUNCH(6, 2, true, 17 + 64); break;
-    case 87: PT_LAUNCH(6, 2, true, 17 + 512); break;   // ... + time-line trace
-    case 88: PT_LAUNCH(3, 2, true, 17); break;
 #define PTP_LAUNCH(POLY, MODE)                                                                                                   \
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_ptp_kernel<POLY, MODE>), PT_SMEM);                                                                \
@@ -1500,24 +1190,34 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     const long long ctas = pp.total_items < (long long)sm_count() ? pp.total_items : (long long)sm_count();                         \
     B200_CUDA_OK(b200_launch(flash_attn_ptp_kernel<POLY, MODE>, dim3((unsigned)ctas), dim3(640), PT_SMEM, st, mq, mk, mv, p, pp));  \
   }
-    case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs, otherwise variant 65
-    case 91: PTP_LAUNCH(8, 0); break;
-    case 92: PTP_LAUNCH(4, 0); break;
-    case 93: PTP_LAUNCH(0, 0); break;
+  // MODE bits of flash_attn_pt_kernel: 1 no "- C", 2/4 ablations, 8 warp-elected arrivals, 16 score preload, 32 chunked P hand-over,
+  // 64 late P-buffer wait, 128 x64 tcgen05.ld, 256 sequential loads, 512 time-line trace
+  switch (variant) {
+    case -1:                                     // product path
+      if (persistent_on && ntiles <= FA_PERSISTENT_MAX_TILES) PTP_LAUNCH(6, 0)
+      else PT_LAUNCH(6, 2, false, 17)
+      break;
+    case 12: PP_LAUNCH(0, 2); break;             // round-1 default: P through shared memory, 16 softmax warps (1.66 ms)
+    case 20: PT_LAUNCH(0, 2, false, 0); break;   // P in tensor memory (1.53 ms)
+    case 41: PT_LAUNCH(8, 2, false, 1); break;   // ... P = exp2(S), 1/8 polynomial exp2 (1.42 ms with the wait hint)
+    case 54: PT_LAUNCH(8, 2, false, 9); break;   // ... one barrier arrival per warp (no change)
+    case 60: PT_LAUNCH(8, 2, false, 41); break;  // ... P handed over in 32-key chunks (1.37 ms)
+    case 59: PT_LAUNCH(8, 2, false, 17); break;  // scores preloaded, S released before the first exponential (1.23 ms)
+    case 65: PT_LAUNCH(6, 2, false, 17); break;  // ... 1/6 polynomial: the one-shot default (1.20 ms)
+    case 66: PT_LAUNCH(0, 2, false, 17); break;  // ... all exponentials on MUFU (1.29 ms)
+    case 71: PT_LAUNCH(8, 2, false, 81); break;  // ... late P-buffer wait (1.21 ms)
+    case 78: PT_LAUNCH(6, 2, false, 145); break; // ... one x64 tcgen05.ld (no change)
+    case 82: PT_LAUNCH(6, 2, true, 17); break;   // ... MUFU token between the two query-tile groups (1.41 ms: slower)
+    case 69: PT_LAUNCH(0, 2, false, 19); break;  // bottleneck experiment: preload, no MUFU (1.10 ms, wrong results)
+    case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;   // default + time-line trace (tools/attn_trace.py)
+    case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs at any length
     case 94: PTP_LAUNCH(0, 2); break;            // bottleneck experiment: persistent, no MUFU
-#undef PTP_LAUNCH
-    case 60: PT_LAUNCH(8, 2, false, 41); break;  // warp arrivals + P in 32-key chunks
-    case 61: PT_LAUNCH(8, 2, false, 57); break;  // warp arrivals + chunks + preload
-    case 62: PT_LAUNCH(8, 2, false, 33); break;  // chunks only
-    case 63: PT_LAUNCH(4, 1, false, 41); break;  // 8 softmax warps: warp arrivals + chunks  // bottleneck experiment: warp arrivals, neither MUFU nor TMEM reads
-    case 50: PT_LAUNCH(0, 2, false, 3); break;   // bottleneck experiment: no MUFU
-    case 51: PT_LAUNCH(0, 2, false, 5); break;   // bottleneck experiment: no TMEM reads
-    case 52: PT_LAUNCH(0, 2, false, 7); break;   // bottleneck experiment: neither
-#undef PT_LAUNCH
-    default: PP_LAUNCH(0, 1); break;   // ping-pong: two query tiles per CTA, all exponentials on MUFU
-#undef PP_LAUNCH
+    case 95: PTP_LAUNCH(6, 4); break;            // persistent + per-CTA rotated key-tile order (no change)
+    default: B200_REQUIRE(false, "attention: unknown B200_IMAGEN_FA_VARIANT=%d", variant);
   }
-#undef FA_LAUNCH
+#undef PTP_LAUNCH
+#undef PT_LAUNCH
+#undef PP_LAUNCH
   B200_LAUNCH_OK();
   if (trace_path && p.trace) {
     static long long host[TRACE_WORDS];
