@@ -392,7 +392,7 @@ def main():
         # MUFU floor of head-dim-64 attention: one exp2 per score, 16 exp2/clk/SM measured (profiles/r01_mufu_ex2_microbench.txt)
         n_exp = R * 8 * 4096 * ((4096 + 39 + 127) // 128 * 128)
         mufu_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
-        line['roofline'] = {'kernel': 'flash_attn_pt_kernel<6,2,0,17> (tcgen05 multi-query self-attention, P in tensor memory, scores preloaded; 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
+        line['roofline'] = {'kernel': 'flash_attn_pt_kernel<4,2,0,1105> (tcgen05 multi-query self-attention, P in tensor memory, scores preloaded, S MMAs on a third issuer thread; 64x64 level: 8*4096 query rows x 4135 keys x d64 per sample)',
                             'bound': 'tensor', 'achieved': att_tflops, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': att_tflops / pk['tensor_burst'],
                             'traffic': 261.9e6, 'traffic_source': 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r02_ncu_flash_attn_pt_summary.txt); algorithmic q+o+k+v = 285 MB',
                             'ms_per_launch': att_ms, 'algorithmic_gflop_per_launch': ATTN_L0_GFLOP_PER_SAMPLE * R,

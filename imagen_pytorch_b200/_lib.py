@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libb200imagen.so')
+LIB_PATH = os.environ.get('B200_IMAGEN_LIB') or os.path.join(_HERE, 'csrc', 'libb200imagen.so')   # the override is for A/B runs of two builds
 
 MAX_SRC, MAX_SEG = 4, 24
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2

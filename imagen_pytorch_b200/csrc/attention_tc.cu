@@ -26,7 +26,7 @@ namespace {
 constexpr int FA_BM = 128;
 constexpr int FA_BN = 128;
 constexpr int FA_D = 64;
-constexpr int FA_PERSISTENT_MAX_TILES = 17;  // persistent kernel up to 2176 keys: 13.7 vs 15.5 us per CTA item at 9 tiles, 44.2 vs 43.4 at 33 (profiles/r02_attention_persistent_sweep.txt)
+constexpr int FA_PERSISTENT_MAX_TILES = 13;  // persistent kernel up to 1664 keys: 3.4 us + 1.20 us per key tile per item against 5.1 + 1.07 one-shot (profiles/r02_attention_elect_split_sweep.txt)
 constexpr int FA_DEFAULT_WAIT_NS = 100;  // barrier waits park instead of spinning (1.58 -> 1.41 ms, profiles/r02_attention_wait_hint_sweep.txt)
 constexpr int FA_Q_BYTES = FA_BM * FA_D * 2;        // 16 KB
 constexpr int FA_K_BYTES = FA_BN * FA_D * 2;        // 16 KB
@@ -122,11 +122,11 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see elect_one in ptx.cuh)
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: both query tiles, then the K/V ring
       mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
       for (int g = 0; g < 2; ++g) {
@@ -149,7 +149,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer of group g
       const int g = warp - 1;
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
@@ -366,7 +366,11 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   constexpr bool PCH = (MODE & 32) != 0;
   constexpr bool LATE = (MODE & 64) != 0;
   constexpr bool TRACE = (MODE & 512) != 0;
-  const bool traced = TRACE && p.trace != nullptr && (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == p.trace_cta && (threadIdx.x & 31) == 0;
+  // MODE bit 10: the S = Q K^T MMAs of BOTH groups are issued by a third thread (warp 3).  One issuer thread per group was the
+  // bottleneck of the kernel: ~20 dependent operations per key tile (4 barrier waits, 12 MMAs with their descriptors, 4 commits) at
+  // ~100 cycles each = the 2100-2250 cycles per tile that remained with the exponentials removed.
+  constexpr bool SPLIT = (MODE & 1024) != 0;
+  const bool traced = TRACE && p.trace != nullptr && (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == p.trace_cta && ((threadIdx.x >> 5) < 4 || (threadIdx.x & 31) == 0);
 #define FA_TR(j_, slot_)                                                                                   \
   do {                                                                                                     \
     if (TRACE && traced && (j_) < 64) p.trace[(((threadIdx.x >> 5) * 64 + (j_)) << 3) + (slot_)] = clock64(); \
@@ -397,11 +401,11 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see elect_one in ptx.cuh)
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: both query tiles, then the K/V ring
       mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
       for (int g = 0; g < 2; ++g) {
@@ -426,12 +430,14 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer of group g
       const int g = warp - 1;
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+      const uint64_t kdesc0 = make_sw128_kmajor_desc(smem_u32(sKV));                           // + stage * (FA_KV_BYTES >> 4)
+      const uint64_t vdesc0 = make_sw128_mnmajor_desc(smem_u32(sKV + FA_K_BYTES), 1024, 1024);
       auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once group g has pulled S_g(j-1) into registers
         const int st = j % PT_STAGES;
         FA_TR(j, 0);
@@ -440,18 +446,21 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         mbar_wait_sleep(&s_empty[g], (uint32_t)((j & 1) ^ 1), p.wait_ns);
         FA_TR(j, 2);
         tc_fence_after();
-        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
+        const uint64_t bdesc = kdesc0 + (uint64_t)(st * (FA_KV_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k)
           umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_full[g]);
       };
-      mbar_wait_sleep(q_full, 0, p.wait_ns);
-      issue_s(0);
+      if (!SPLIT) {
+        mbar_wait_sleep(q_full, 0, p.wait_ns);
+        issue_s(0);
+      }
       for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) issue_s(j + 1);
+        if (!SPLIT && j + 1 < ntiles) issue_s(j + 1);
         const int st = j % PT_STAGES;
-        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+        if (SPLIT) mbar_wait_sleep(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1), p.wait_ns);   // V_j has landed (this thread did not issue S_j)
+        const uint64_t vdesc = vdesc0 + (uint64_t)(st * (FA_KV_BYTES >> 4));
         // the first keys are multiplied while the later ones are exponentiated: halves in order, or (PCH) chunk 0 of both halves first
         for (int u = 0; u < (PCH ? 4 : 2); ++u) {
           const int hf = !PCH ? u : (SUB == 2 ? (u & 1) : (u >> 1)), ci = !PCH ? 0 : (SUB == 2 ? (u >> 1) : (u & 1));   // production order
@@ -464,7 +473,7 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
           for (int k = (PCH ? 2 * ci : 0); k < (PCH ? 2 * ci + 2 : 4); ++k) {
             // A: 16 keys = 8 packed columns of this half's P block; B: 16 key rows of V (MN-major, 2 KB)
             const uint32_t a_tmem = tmem_base + TM_P + (uint32_t)(g * 64 + hf * 32 + k * 8);
-            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((hf * 4 + k) * 16 * 128), 1024, 1024);
+            const uint64_t bdesc = vdesc + (uint64_t)((hf * 4 + k) * (16 * 128 >> 4));
             umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, (j | u | (k & 1) | (PCH ? 0 : k)) != 0 ? 1u : 0u);
           }
           umma_commit(&p_empty[pb]);
@@ -473,6 +482,32 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
         FA_TR(j, 7);
       }
       umma_commit(&o_full[g]);
+    }
+  } else if (SPLIT && warp == 3) {
+    if (elect_one()) {
+      // ---------------- S issuer of both groups
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qdesc0 = make_sw128_kmajor_desc(smem_u32(sQ));
+      const uint64_t kdesc0 = make_sw128_kmajor_desc(smem_u32(sKV));
+      mbar_wait_sleep(q_full, 0, p.wait_ns);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % PT_STAGES;
+        FA_TR(j, 0);
+        mbar_wait_sleep(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1), p.wait_ns);
+        const uint64_t bdesc = kdesc0 + (uint64_t)(st * (FA_KV_BYTES >> 4));
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          FA_TR(j, 1 + 3 * g);
+          mbar_wait_sleep(&s_empty[g], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // group g has pulled S_g(j-1) into registers
+          FA_TR(j, 2 + 3 * g);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < FA_D / 16; ++k)
+            umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc0 + (uint64_t)(g * (FA_Q_BYTES >> 4) + 2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+          FA_TR(j, 3 + 3 * g);
+        }
+      }
     }
   } else if (warp >= 4) {
     // ---------------- softmax / epilogue: group g, thread = (query row of that group, 64-key half if SUB == 2)
@@ -622,6 +657,217 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// "Dual" softmax: every softmax thread serves BOTH query tiles.  The time line of the kernel above (tools/attn_trace.py) shows each
+// softmax warp busy for ~1500 of the 2430 cycles of a key tile and waiting for the rest (S ready, TMEM load, the P V MMA of the
+// previous tile freeing its P buffer) -- and the two query-tile groups wait at the same time, so the MUFU pipe idles then.  Here a
+// thread owns (query row r, 32-key quarter c) of tile A AND of tile B: per key tile it pulls both 32-score slices into registers
+// (releasing S_A and S_B), then exponentiates one tile's slice, hands that P quarter to the issuer, and does the other tile's slice.
+// By the time it returns to a tile, that tile's next S has long been computed and its P quarter long been multiplied, so in steady
+// state no barrier wait blocks; odd quarters start with tile B, even ones with tile A, so P quarters reach both issuers evenly.
+// TMEM as above; P quarter c of group g = 16 columns at 384 + 64 g + 16 c.  The P V product runs per quarter (K = 32: two MMAs).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PD_SMEM = 2 * FA_Q_BYTES + PT_STAGES * FA_KV_BYTES + 1024 + 512 + 4096;   // + barriers + [2][4][128] partial row sums
+
+template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results)
+__global__ void __launch_bounds__(640, 1)
+flash_attn_pd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p) {
+  pdl_trigger();
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;                                   // [2] query tiles
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;                   // [PT_STAGES] {K, V}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + PT_STAGES * FA_KV_BYTES);
+  uint64_t* q_full = bars;                              // [1]
+  uint64_t* kv_full = bars + 1;                         // [PT_STAGES]
+  uint64_t* kv_empty = kv_full + PT_STAGES;             // [PT_STAGES] (count 2: both groups' P V MMAs)
+  uint64_t* s_full = kv_empty + PT_STAGES;              // [group]
+  uint64_t* s_empty = s_full + 2;                       // [group] (count 512: every softmax thread reads both S tiles)
+  uint64_t* p_full = s_empty + 2;                       // [group][quarter] (count 128)
+  uint64_t* p_empty = p_full + 8;                       // [group][quarter]
+  uint64_t* o_full = p_empty + 8;                       // [group]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* sL = reinterpret_cast<float*>(bars + 64);      // [group][quarter][128] partial row sums
+  static_assert(1 + 2 * PT_STAGES + 2 + 2 + 8 + 8 + 2 + 1 <= 64, "barrier block is 512 bytes");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * (2 * FA_BM);
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
+  const int nq_last = (p.n_keys - (ntiles - 1) * FA_BN + 31) >> 5;   // live 32-key quarters of the last tile (1..4)
+  constexpr uint32_t TM_O = 256, TM_P = 384;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 512);
+      mbar_init(&o_full[g], 1);
+      for (int c = 0; c < 4; ++c) { mbar_init(&p_full[4 * g + c], 128); mbar_init(&p_empty[4 * g + c], 1); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, FA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see elect_one in ptx.cuh)
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- TMA producer: both query tiles, then the K/V ring
+      mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
+      for (int g = 0; g < 2; ++g) {
+        if (p.q_heads_first) tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, h, row0 + g * FA_BM, b);
+        else tma_load_4d(sQ + g * FA_Q_BYTES, &mapQ, q_full, 0, row0 + g * FA_BM, h, b);
+      }
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % PT_STAGES;
+        const uint32_t n = (uint32_t)(j / PT_STAGES);
+        mbar_wait_sleep(&kv_empty[st], (n & 1u) ^ 1u, p.wait_ns);
+        mbar_expect_tx(&kv_full[st], FA_KV_BYTES);
+        uint8_t* dst = sKV + st * FA_KV_BYTES;
+        if (p.kv_heads_first) {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, h, j * FA_BN, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, h, j * FA_BN, b);
+        } else {
+          tma_load_4d(dst, &mapK, &kv_full[st], 0, j * FA_BN, h, b);
+          tma_load_4d(dst + FA_K_BYTES, &mapV, &kv_full[st], 0, j * FA_BN, h, b);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    if (elect_one()) {
+      // ---------------- MMA issuer of group g
+      const int g = warp - 1;
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qdesc = make_sw128_kmajor_desc(smem_u32(sQ + g * FA_Q_BYTES));
+      auto issue_s = [&](int j) {               // S_g(j) = Q_g K_j^T once every softmax thread has pulled S_g(j-1) into registers
+        const int st = j % PT_STAGES;
+        mbar_wait_sleep(&kv_full[st], (uint32_t)((j / PT_STAGES) & 1), p.wait_ns);
+        mbar_wait_sleep(&s_empty[g], (uint32_t)((j & 1) ^ 1), p.wait_ns);
+        tc_fence_after();
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sKV + st * FA_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait_sleep(q_full, 0, p.wait_ns);
+      issue_s(0);
+      uint32_t acc = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        const int st = j % PT_STAGES;
+        const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
+        for (int u = 0; u < 4; ++u) {           // quarters in the order the softmax threads produce them for this group
+          const int c = ((u & 1) << 1) | ((u >> 1) ^ g);   // g = 0: 0, 2, 1, 3;  g = 1: 1, 3, 0, 2
+          if (j == ntiles - 1 && c >= nq_last) continue;
+          mbar_wait_sleep(&p_full[4 * g + c], (uint32_t)(j & 1), p.wait_ns);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            // A: 16 keys = 8 packed columns of this quarter's P block; B: 16 key rows of V (MN-major, 2 KB)
+            const uint32_t a_tmem = tmem_base + TM_P + (uint32_t)(g * 64 + c * 16 + k * 8);
+            const uint64_t bdesc = make_sw128_mnmajor_desc(v_addr + (uint32_t)((c * 2 + k) * 16 * 128), 1024, 1024);
+            umma_bf16_ts(tmem_base + TM_O + (uint32_t)(g * FA_D), a_tmem, bdesc, idesc_pv, acc);
+            acc = 1u;
+          }
+          umma_commit(&p_empty[4 * g + c]);
+        }
+        umma_commit(&kv_empty[st]);             // one of the two arrivals that free K_j / V_j
+      }
+      umma_commit(&o_full[g]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax / epilogue: thread = (query row r of BOTH tiles, 32-key quarter c)
+    const int q = warp & 3;
+    const int c = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int g0 = c & 1, g1 = g0 ^ 1;                  // the tile this thread exponentiates first / second
+    float l0 = 0.f, l1 = 0.f;                           // row sums of tile g0 / g1 over this quarter
+    for (int j = 0; j < ntiles; ++j) {
+      if (j == ntiles - 1 && c >= nq_last) break;       // no valid key in this quarter of the last tile
+      const int kb = j * FA_BN + c * 32;
+      const bool ragged = kb + 32 > p.n_keys;
+      uint32_t s0[32], s1[32];
+      mbar_wait_sleep(&s_full[g0], (uint32_t)(j & 1), p.wait_ns);
+      tc_fence_after();
+      tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g0 * FA_BN + c * 32), s0);
+      mbar_wait_sleep(&s_full[g1], (uint32_t)(j & 1), p.wait_ns);
+      tc_fence_after();
+      tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g1 * FA_BN + c * 32), s1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(s0[i])); asm volatile("" : "+r"(s1[i])); }   // pin behind the wait
+      tc_fence_before();
+      mbar_arrive(&s_empty[g0]);                        // this thread's share of both S tiles is in registers
+      mbar_arrive(&s_empty[g1]);
+      uint32_t pk[16];
+      mbar_wait_sleep(&p_empty[4 * g0 + c], (uint32_t)((j & 1) ^ 1), p.wait_ns);   // P V of tile j-1 has read this quarter
+      tc_fence_after();
+      if (ragged) pt_chunk32<POLY, 1 | (MODE & 2), true>(s0, 0.f, kb, p.n_keys, pk, l0);
+      else pt_chunk32<POLY, 1 | (MODE & 2), false>(s0, 0.f, kb, p.n_keys, pk, l0);
+      tmem_st16(tmem_base + lane_off + TM_P + (uint32_t)(g0 * 64 + c * 16), pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[4 * g0 + c]);
+      mbar_wait_sleep(&p_empty[4 * g1 + c], (uint32_t)((j & 1) ^ 1), p.wait_ns);
+      tc_fence_after();
+      if (ragged) pt_chunk32<POLY, 1 | (MODE & 2), true>(s1, 0.f, kb, p.n_keys, pk, l1);
+      else pt_chunk32<POLY, 1 | (MODE & 2), false>(s1, 0.f, kb, p.n_keys, pk, l1);
+      tmem_st16(tmem_base + lane_off + TM_P + (uint32_t)(g1 * 64 + c * 16), pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[4 * g1 + c]);
+    }
+    // ---- O / l -> global: the four quarter threads of a row add their sums; each stores 16 channels of both tiles
+    mbar_wait_sleep(&o_full[0], 0, p.wait_ns);
+    mbar_wait_sleep(&o_full[1], 0, p.wait_ns);
+    tc_fence_after();
+    sL[(g0 * 4 + c) * FA_BM + r] = l0;
+    sL[(g1 * 4 + c) * FA_BM + r] = l1;
+    asm volatile("bar.sync 1, 512;" ::: "memory");      // the 16 softmax warps
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float l = (sL[(g * 4 + 0) * FA_BM + r] + sL[(g * 4 + 1) * FA_BM + r]) + (sL[(g * 4 + 2) * FA_BM + r] + sL[(g * 4 + 3) * FA_BM + r]);
+      const float inv = 1.f / l;
+      uint32_t orr[16];
+      tmem_ld16_nowait(tmem_base + lane_off + TM_O + (uint32_t)(g * FA_D + c * 16), orr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(orr[i]));
+      const int row = row0 + g * FA_BM + r;
+      if (row < p.rows) {
+        __nv_bfloat16* orow = p.o + (long long)b * p.q_bs + (long long)h * p.q_hs + (long long)row * p.q_rs + c * 16;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(orr[8 * t + 0]) * inv, __uint_as_float(orr[8 * t + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(orr[8 * t + 2]) * inv, __uint_as_float(orr[8 * t + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(orr[8 * t + 4]) * inv, __uint_as_float(orr[8 * t + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(orr[8 * t + 6]) * inv, __uint_as_float(orr[8 * t + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 8 * t) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // PERSISTENT form of the kernel above (its measured default configuration: 16 softmax warps, scores preloaded, P = exp2(S), P in
 // tensor memory).  tools/attn_keys_scan.py: a CTA of the one-shot kernel costs 5.4 us of launch / prologue / pipeline ramp / epilogue
 // plus 1.15 us per key tile -- 12 % of the 64x64-level launch (33 tiles), 35 % of the 32x32-level one (9 tiles).  Here one CTA per SM
@@ -637,7 +883,7 @@ struct FaPersist {
   long long total_items;   // B * n_heads * pairs_per_head
 };
 
-template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results); bit 2 = per-CTA rotated key-tile order
+template <int POLY, int MODE>   // MODE: bit 1 = no MUFU (bottleneck experiment, wrong results); bit 2 = per-CTA rotated key-tile order; bit 3 = S MMAs issued by a third thread
 __global__ void __launch_bounds__(640, 1)
 flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FaParams p, const __grid_constant__ FaPersist pp) {
@@ -661,6 +907,7 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   float* sL = reinterpret_cast<float*>(bars + 64);      // [group][sub][128] partial row sums
   static_assert(2 + 2 * PT_STAGES + 2 + 2 + 4 + 4 + 2 + 2 + 1 <= 64, "barrier block is 512 bytes");
 
+  constexpr bool SPLIT = (MODE & 8) != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = (p.n_keys + FA_BN - 1) / FA_BN;
   const int dead = ((ntiles - 1) * FA_BN + 64 >= p.n_keys) ? 1 : 0;   // the last tile's second 64-key half holds no valid key
@@ -675,7 +922,7 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 2);
+    mbar_init(q_empty, SPLIT ? 1 : 2);
     for (int s = 0; s < PT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
@@ -690,11 +937,11 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see elect_one in ptx.cuh)
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer
       uint32_t T = 0;                                   // key tiles loaded by this CTA so far
       int n = 0;
@@ -725,7 +972,7 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       }
     }
   } else if (warp == 1 || warp == 2) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer of group g
       const int g = warp - 1;
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
@@ -747,12 +994,15 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           umma_commit(&s_full[g]);
           if (j == ntiles - 1) umma_commit(q_empty);    // Q of this item is no longer needed by this group
         };
-        mbar_wait_sleep(q_full, (uint32_t)(n & 1), p.wait_ns);
-        issue_s(0);
+        if (!SPLIT) {
+          mbar_wait_sleep(q_full, (uint32_t)(n & 1), p.wait_ns);
+          issue_s(0);
+        }
         for (int j = 0; j < ntiles; ++j) {
-          if (j + 1 < ntiles) issue_s(j + 1);
+          if (!SPLIT && j + 1 < ntiles) issue_s(j + 1);
           const uint32_t T = T0 + (uint32_t)j;
           const int st = (int)(T % PT_STAGES);
+          if (SPLIT) mbar_wait_sleep(&kv_full[st], (T / PT_STAGES) & 1u, p.wait_ns);   // V_j has landed (this thread did not issue S_j)
           const uint32_t v_addr = smem_u32(sKV + st * FA_KV_BYTES + FA_K_BYTES);
           for (int hf = 0; hf < 2; ++hf) {              // the first 64 keys are multiplied while the second 64 are exponentiated
             if (hf == 1 && dead && j == jd) break;
@@ -772,6 +1022,33 @@ flash_attn_ptp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           umma_commit(&kv_empty[st]);                   // one of the two arrivals that free K_j / V_j
         }
         umma_commit(&o_full[g]);
+      }
+    }
+  } else if (SPLIT && warp == 3) {
+    if (elect_one()) {
+      // ---------------- S issuer of both groups
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qdesc0 = make_sw128_kmajor_desc(smem_u32(sQ));
+      const uint64_t kdesc0 = make_sw128_kmajor_desc(smem_u32(sKV));
+      uint32_t T = 0;
+      int n = 0;
+      for (long long it = blockIdx.x; it < pp.total_items; it += gridDim.x, ++n) {
+        mbar_wait_sleep(q_full, (uint32_t)(n & 1), p.wait_ns);
+        for (int j = 0; j < ntiles; ++j, ++T) {
+          const int st = (int)(T % PT_STAGES);
+          mbar_wait_sleep(&kv_full[st], (T / PT_STAGES) & 1u, p.wait_ns);
+          const uint64_t bdesc = kdesc0 + (uint64_t)(st * (FA_KV_BYTES >> 4));
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait_sleep(&s_empty[g], (T & 1u) ^ 1u, p.wait_ns);   // group g has pulled its previous S into registers
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < FA_D / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(g * FA_BN), qdesc0 + (uint64_t)(g * (FA_Q_BYTES >> 4) + 2 * k), bdesc + (uint64_t)(2 * k), idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[g]);
+          }
+          if (j == ntiles - 1) umma_commit(q_empty);    // Q of this item is no longer needed
+        }
       }
     }
   } else if (warp >= 4) {
@@ -936,13 +1213,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see elect_one in ptx.cuh)
   pdl_wait();
   // TMEM columns: accumulators on 64-column boundaries (S_s at 128 s, O_s at 128 s + 64), the packed P tiles behind them (384 + 32 s)
   constexpr uint32_t SLOT_COLS = 128, P_BASE = 384;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: K/V of all heads whenever the sample changes, then one Q tile per item
       int cur_b = -1, epoch = 0;
       for (int i = 0; i < n_items; ++i) {
@@ -966,7 +1243,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(XA_KEYS >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
@@ -1194,8 +1471,8 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
   // 64 late P-buffer wait, 128 x64 tcgen05.ld, 256 sequential loads, 512 time-line trace
   switch (variant) {
     case -1:                                     // product path
-      if (persistent_on && ntiles <= FA_PERSISTENT_MAX_TILES) PTP_LAUNCH(6, 0)
-      else PT_LAUNCH(6, 2, false, 17)
+      if (persistent_on && ntiles <= FA_PERSISTENT_MAX_TILES) PTP_LAUNCH(4, 8)
+      else PT_LAUNCH(4, 2, false, 17 + 1024 + 64)
       break;
     case 12: PP_LAUNCH(0, 2); break;             // round-1 default: P through shared memory, 16 softmax warps (1.66 ms)
     case 20: PT_LAUNCH(0, 2, false, 0); break;   // P in tensor memory (1.53 ms)
@@ -1210,9 +1487,35 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     case 82: PT_LAUNCH(6, 2, true, 17); break;   // ... MUFU token between the two query-tile groups (1.41 ms: slower)
     case 69: PT_LAUNCH(0, 2, false, 19); break;  // bottleneck experiment: preload, no MUFU (1.10 ms, wrong results)
     case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;   // default + time-line trace (tools/attn_trace.py)
+    case 110: PT_LAUNCH(6, 2, false, 17 + 1024); break;  // S MMAs of both groups issued by a third thread
+    case 111: PT_LAUNCH(8, 2, false, 17 + 1024); break;
+    case 112: PT_LAUNCH(4, 2, false, 17 + 1024); break;
+    case 113: PT_LAUNCH(0, 2, false, 17 + 1024); break;
+    case 114: PT_LAUNCH(0, 2, false, 19 + 1024); break;  // bottleneck experiment: ... no MUFU
+    case 115: PT_LAUNCH(6, 2, false, 17 + 1024 + 512); break;  // ... + time-line trace
+    case 116: PT_LAUNCH(6, 2, false, 17 + 1024 + 64); break;   // ... + late P-buffer wait
+    case 117: PT_LAUNCH(3, 2, false, 17 + 1024); break;
+    case 118: PT_LAUNCH(4, 2, false, 17 + 1024 + 64); break;   // split-S + late P-buffer wait, 1/4 polynomial
+    case 119: PT_LAUNCH(3, 2, false, 17 + 1024 + 64); break;
+    case 124: PT_LAUNCH(2, 2, false, 17 + 1024); break;
+#define PD_LAUNCH(POLY, MODE)                                                                                                    \
+  {                                                                                                                                \
+    B200_SMEM_OPT_IN((flash_attn_pd_kernel<POLY, MODE>), PD_SMEM);                                                                 \
+    B200_CUDA_OK(b200_launch(flash_attn_pd_kernel<POLY, MODE>, grid2, dim3(640), PD_SMEM, st, mq, mk, mv, p));                      \
+  }
+    case 100: PD_LAUNCH(6, 0); break;            // dual softmax: every thread serves both query tiles
+    case 101: PD_LAUNCH(8, 0); break;
+    case 102: PD_LAUNCH(4, 0); break;
+    case 103: PD_LAUNCH(0, 0); break;
+    case 104: PD_LAUNCH(0, 2); break;            // bottleneck experiment: dual, no MUFU
+#undef PD_LAUNCH
     case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs at any length
     case 94: PTP_LAUNCH(0, 2); break;            // bottleneck experiment: persistent, no MUFU
     case 95: PTP_LAUNCH(6, 4); break;            // persistent + per-CTA rotated key-tile order (no change)
+    case 120: PTP_LAUNCH(6, 8); break;           // persistent + third issuer thread for S
+    case 121: PTP_LAUNCH(4, 8); break;
+    case 122: PTP_LAUNCH(3, 8); break;
+    case 123: PTP_LAUNCH(0, 10); break;          // bottleneck experiment: ... no MUFU
     default: B200_REQUIRE(false, "attention: unknown B200_IMAGEN_FA_VARIANT=%d", variant);
   }
 #undef PTP_LAUNCH

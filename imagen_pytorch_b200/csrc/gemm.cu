@@ -765,11 +765,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: no ELECT / R2UR.BROADCAST loop around every tcgen05 instruction
   pdl_wait();      // barriers, TMEM and descriptors are set up: from here on the previous grid's results are read
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
@@ -804,7 +804,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer (InstrDescriptor: c_format F32 [4,6)=1, a/b BF16 [7,10)=[10,13)=1,
       // K-major both, N>>3 at [17,23), M>>4 at [24,29))
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -955,10 +955,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   tc_fence_before();
   cluster_sync_all();                      // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: no ELECT / R2UR.BROADCAST loop around every tcgen05 instruction
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer (both CTAs)
       int stage = 0;
       uint32_t phase = 0;
@@ -991,7 +991,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       // ---------------- MMA issuer (rank 0 only): M = 256 over the pair, N = BN
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0, acc = 0;
@@ -1113,11 +1113,11 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: no ELECT / R2UR.BROADCAST loop around every tcgen05 instruction
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: this rank's share of the K chunks
       const int wblk = tile % p.tiles_w;
       const int hblk = (tile / p.tiles_w) % p.tiles_h;
@@ -1142,7 +1142,7 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KS_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -1268,11 +1268,11 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform: no ELECT / R2UR.BROADCAST loop around every tcgen05 instruction
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- TMA producer: weight tile {64 k, 128 channels} + pixel tile {64 ch, bw, bh, bb} shifted by the tap
       int stage = 0;
       uint32_t phase = 0;
@@ -1299,7 +1299,7 @@ conv_gemm_tcT_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------- MMA issuer: M = 128 (channels), N = 256 (pixels), both operands K-major
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T_BP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0, acc = 0;

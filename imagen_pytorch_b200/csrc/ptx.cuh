@@ -159,6 +159,20 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
                : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  ptxas recognises the elected predicate as "exactly one thread": tcgen05.mma / commit / TMA
+// issued under it compile to single instructions, whereas under `if (lane == 0)` every one of them is wrapped in an
+// ELECT / BRA.U.ANY serialisation loop over the (unknown to ptxas) set of active lanes.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
