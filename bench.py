@@ -399,7 +399,7 @@ def main():
                             'peak_source': f"{pk['src']} burst bf16 (kernel timed alone)",
                             'mufu_floor_ms': mufu_ms, 'frac_of_mufu_floor': mufu_ms / att_ms}
         conv_ms, conv_gflop = time_conv_kernel(R, device)
-        line['roofline_conv'] = {'kernel': 'conv_gemm_tcT_kernel<4> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64, transposed: weights = M operand, 256 pixels = N operand)', 'bound': 'tensor',
+        line['roofline_conv'] = {'kernel': 'conv_gemm_tc_kernel<128,6,1,8,0> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64, 128 x 128 tiles, MMAs issued under elect.sync)', 'bound': 'tensor',
                                  'achieved': conv_gflop / conv_ms, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': conv_gflop / conv_ms / pk['tensor_burst'],
                                  'traffic': 34.0e6, 'ms_per_launch': conv_ms, 'algorithmic_gflop_per_launch': conv_gflop,
                                  'note': 'L2 flushed between launches; dram traffic from ncu = 33.9 MB read (input 33.5 MB read once), output stays in L2'}

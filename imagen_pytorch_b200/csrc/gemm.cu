@@ -1758,7 +1758,9 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   B200_REQUIRE(enc != nullptr, "conv_gemm: cuTensorMapEncodeTiled not available from the driver");
   // ---- transposed kernel for MMA-bound layers with <= 128 output channels (see conv_gemm_tcT_kernel)
   {
-    static const bool t_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_T"); return ev == nullptr || atoi(ev) != 0; }();
+    // off by default since the MMAs are issued under elect.sync: the 128 x 128 kernel went from 878 to 1140 TFLOP/s MMA-only and beats the
+    // transposed one (46.1 vs 48.1 us on the 64x64 conv, profiles/r02_gemm_after_elect.txt); B200_IMAGEN_GEMM_T=1 selects it
+    static const bool t_on = [] { const char* ev = getenv("B200_IMAGEN_GEMM_T"); return ev != nullptr && atoi(ev) != 0; }();
     const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const long long Mll = (long long)B * H * W;
     const bool t_epi = e.out_mode == B200_OUT_BF16 && e.split_col == 0 && e.rows_per_group == 0 && e.l2_cols == 0 && e.dup_rows == 0 && e.norm1 == 0 &&
@@ -1822,11 +1824,13 @@ extern "C" int b200_conv_gemm(const b200_src* srcs, int nsrc, const b200_seg* se
   if (p.Npad <= 64) BN = p.Npad;
   else if (pair) BN = (p.Npad % 256 == 0 && (long long)((ntiles + 1) / 2) * (p.Npad / 256) >= sm_count() / 2) ? 256 : 128;
   else if (p.Npad % 256 == 0) {
-    // 128 x 128 MMAs are bound by shared-memory operand reads (878 TFLOP/s issue-only on B200 vs 1398 for 128 x 256,
-    // profiles/r01_gemm_bottleneck.txt): cost of a tile ~ BN / rate(BN); pick the width with fewer (waves x tile cost)
+    // MMA-only rates measured on B200 (tools/gemm_bench.py, debug 5): 1140 TFLOP/s for 128 x 128 tiles, 1398 for 128 x 256
+    // (profiles/r02_gemm_after_elect.txt; 878 / 1398 before the issue loop was fixed): cost of a tile ~ BN / rate(BN);
+    // pick the width with fewer (waves x tile cost)
     const long long t128 = (long long)ntiles * (p.Npad / 128), t256 = (long long)ntiles * (p.Npad / 256);
     const long long sms = sm_count();
-    const double c128 = (double)((t128 + sms - 1) / sms) * (128.0 / 878.0), c256 = (double)((t256 + sms - 1) / sms) * (256.0 / 1398.0);
+    static const double rate128 = [] { const char* e = getenv("B200_IMAGEN_GEMM_RATE128"); return e ? atof(e) : 1140.0; }();   // tuning hook
+    const double c128 = (double)((t128 + sms - 1) / sms) * (128.0 / rate128), c256 = (double)((t256 + sms - 1) / sms) * (256.0 / 1398.0);
     BN = c256 <= c128 ? 256 : 128;
   } else BN = 128;
   if (has_norm) BN = p.Npad;   // one tile spans all channels

@@ -203,9 +203,10 @@ def _ln_ref(x, g):
 
 @pytest.mark.parametrize('case', ['conv3x3_plain', 'conv3x3_res', 'conv3x3_rms_film_only', 'conv3x3_raw_and_ln', 'two_sources_res_rms', 'ragged_96ch_silu', 'linear_k512'])
 def test_transposed_gemm_for_128_output_channels(case):
-    """conv_gemm_tcT_kernel: D^T = W X^T with the weights as the M = 128 operand and 256 pixels as the N operand, epilogue transposed through
-    shared memory; selected by b200_conv_gemm for Npad == 128, K >= 512 and >= one 256-pixel tile per SM.  Same torch fp32 references as the
-    row-major kernel's tests."""
+    """Shapes of conv_gemm_tcT_kernel (D^T = W X^T with the weights as the M = 128 operand and 256 pixels as the N operand, epilogue transposed
+    through shared memory; Npad == 128, K >= 512, >= one 256-pixel tile per SM).  The kernel is opt-in (B200_IMAGEN_GEMM_T=1) since the
+    elect.sync issue fix made the row-major kernel faster: this test runs on whichever kernel the process selects, and
+    test_transposed_kernel_switch re-runs it in a child process with the switch on.  Same torch fp32 references as the row-major tests."""
     cfg = {
         'conv3x3_plain': dict(B=3, H=128, W=128, Cs=[128], N=128, k=3, res=False, n2=0, film=False, raw=True, act=0),
         'conv3x3_res': dict(B=3, H=128, W=128, Cs=[128], N=128, k=3, res=True, n2=0, film=False, raw=True, act=0),
@@ -253,6 +254,20 @@ def test_transposed_gemm_for_128_output_channels(case):
                 y = y * (fr[:, :N] + 1) + fr[:, N:2 * N]
             y = F.silu(y)
         assert_close(out_n, y, 1.2e-2, 1.5e-2, f'{case}: normalised')
+
+
+def test_transposed_kernel_switch():
+    """The opt-in transposed GEMM kernel still passes its parity cases (child process: the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('B200_IMAGEN_GEMM_T') == '1':
+        pytest.skip('already inside the child')
+    env = dict(os.environ, B200_IMAGEN_GEMM_T='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-p', 'no:cacheprovider', __file__, '-m', 'gpu', '-k', 'test_transposed_gemm_for_128_output_channels'],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '7 passed' in r.stdout, r.stdout[-500:]
 
 
 # ------------------------------------------------------------------------------------------------ norms fused into the GEMM epilogue
