@@ -1474,48 +1474,31 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
       if (persistent_on && ntiles <= FA_PERSISTENT_MAX_TILES) PTP_LAUNCH(4, 8)
       else PT_LAUNCH(4, 2, false, 17 + 1024 + 64)
       break;
+    // the measured trail (times of the 64x64-level launch; profiles/r02_attention_*): each variant adds one change to the previous one
     case 12: PP_LAUNCH(0, 2); break;             // round-1 default: P through shared memory, 16 softmax warps (1.66 ms)
     case 20: PT_LAUNCH(0, 2, false, 0); break;   // P in tensor memory (1.53 ms)
-    case 41: PT_LAUNCH(8, 2, false, 1); break;   // ... P = exp2(S), 1/8 polynomial exp2 (1.42 ms with the wait hint)
-    case 54: PT_LAUNCH(8, 2, false, 9); break;   // ... one barrier arrival per warp (no change)
-    case 60: PT_LAUNCH(8, 2, false, 41); break;  // ... P handed over in 32-key chunks (1.37 ms)
+    case 41: PT_LAUNCH(8, 2, false, 1); break;   // P = exp2(S), 1/8 polynomial exp2, suspend-hinted waits (1.42 ms)
+    case 60: PT_LAUNCH(8, 2, false, 41); break;  // P handed over in 32-key chunks, warp-elected arrivals (1.37 ms)
     case 59: PT_LAUNCH(8, 2, false, 17); break;  // scores preloaded, S released before the first exponential (1.23 ms)
-    case 65: PT_LAUNCH(6, 2, false, 17); break;  // ... 1/6 polynomial: the one-shot default (1.20 ms)
-    case 66: PT_LAUNCH(0, 2, false, 17); break;  // ... all exponentials on MUFU (1.29 ms)
-    case 71: PT_LAUNCH(8, 2, false, 81); break;  // ... late P-buffer wait (1.21 ms)
-    case 78: PT_LAUNCH(6, 2, false, 145); break; // ... one x64 tcgen05.ld (no change)
-    case 82: PT_LAUNCH(6, 2, true, 17); break;   // ... MUFU token between the two query-tile groups (1.41 ms: slower)
-    case 69: PT_LAUNCH(0, 2, false, 19); break;  // bottleneck experiment: preload, no MUFU (1.10 ms, wrong results)
-    case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;   // default + time-line trace (tools/attn_trace.py)
-    case 110: PT_LAUNCH(6, 2, false, 17 + 1024); break;  // S MMAs of both groups issued by a third thread
-    case 111: PT_LAUNCH(8, 2, false, 17 + 1024); break;
-    case 112: PT_LAUNCH(4, 2, false, 17 + 1024); break;
-    case 113: PT_LAUNCH(0, 2, false, 17 + 1024); break;
-    case 114: PT_LAUNCH(0, 2, false, 19 + 1024); break;  // bottleneck experiment: ... no MUFU
-    case 115: PT_LAUNCH(6, 2, false, 17 + 1024 + 512); break;  // ... + time-line trace
-    case 116: PT_LAUNCH(6, 2, false, 17 + 1024 + 64); break;   // ... + late P-buffer wait
-    case 117: PT_LAUNCH(3, 2, false, 17 + 1024); break;
-    case 118: PT_LAUNCH(4, 2, false, 17 + 1024 + 64); break;   // split-S + late P-buffer wait, 1/4 polynomial
-    case 119: PT_LAUNCH(3, 2, false, 17 + 1024 + 64); break;
-    case 124: PT_LAUNCH(2, 2, false, 17 + 1024); break;
+    case 65: PT_LAUNCH(6, 2, false, 17); break;  // 1/6 polynomial (1.20 ms; 1.17 ms once issued under elect.sync)
+    case 82: PT_LAUNCH(6, 2, true, 17); break;   // MUFU token between the two query-tile groups (1.41 ms: slower)
+    case 112: PT_LAUNCH(4, 2, false, 17 + 1024); break;        // S MMAs of both groups on a third issuer thread, 1/4 polynomial (1.12 ms)
+    case 118: PT_LAUNCH(4, 2, false, 17 + 1024 + 64); break;   // + late P-buffer wait = the one-shot product path (1.12 ms)
+    case 69: PT_LAUNCH(0, 2, false, 19); break;                // bottleneck experiment: preload, no MUFU (1.10 -> 0.88 ms with elect.sync; wrong results)
+    case 114: PT_LAUNCH(0, 2, false, 19 + 1024); break;        // bottleneck experiment: third issuer thread, no MUFU (0.80 ms)
+    case 81: PT_LAUNCH(6, 2, false, 17 + 512); break;          // variant 65 + time-line trace (tools/attn_trace.py)
+    case 115: PT_LAUNCH(4, 2, false, 17 + 1024 + 512); break;  // variant 112 + time-line trace
 #define PD_LAUNCH(POLY, MODE)                                                                                                    \
   {                                                                                                                                \
     B200_SMEM_OPT_IN((flash_attn_pd_kernel<POLY, MODE>), PD_SMEM);                                                                 \
     B200_CUDA_OK(b200_launch(flash_attn_pd_kernel<POLY, MODE>, grid2, dim3(640), PD_SMEM, st, mq, mk, mv, p));                      \
   }
-    case 100: PD_LAUNCH(6, 0); break;            // dual softmax: every thread serves both query tiles
-    case 101: PD_LAUNCH(8, 0); break;
-    case 102: PD_LAUNCH(4, 0); break;
-    case 103: PD_LAUNCH(0, 0); break;
+    case 100: PD_LAUNCH(6, 0); break;            // dual softmax: every thread serves both query tiles (1.30 ms)
     case 104: PD_LAUNCH(0, 2); break;            // bottleneck experiment: dual, no MUFU
 #undef PD_LAUNCH
-    case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs at any length
-    case 94: PTP_LAUNCH(0, 2); break;            // bottleneck experiment: persistent, no MUFU
-    case 95: PTP_LAUNCH(6, 4); break;            // persistent + per-CTA rotated key-tile order (no change)
-    case 120: PTP_LAUNCH(6, 8); break;           // persistent + third issuer thread for S
-    case 121: PTP_LAUNCH(4, 8); break;
-    case 122: PTP_LAUNCH(3, 8); break;
-    case 123: PTP_LAUNCH(0, 10); break;          // bottleneck experiment: ... no MUFU
+    case 90: PTP_LAUNCH(6, 0); break;            // persistent CTAs at any length (1.16 ms)
+    case 121: PTP_LAUNCH(4, 8); break;           // persistent + third issuer thread = the product path for short key sequences (1.19 ms)
+    case 123: PTP_LAUNCH(0, 10); break;          // bottleneck experiment: persistent, third issuer thread, no MUFU (0.80 ms)
     default: B200_REQUIRE(false, "attention: unknown B200_IMAGEN_FA_VARIANT=%d", variant);
   }
 #undef PTP_LAUNCH

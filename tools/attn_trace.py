@@ -1,5 +1,5 @@
 """Barrier time line of one CTA of the tcgen05 self-attention kernel (development tool).  Runs the 64x64-level launch with the tracing
-variant (B200_IMAGEN_FA_VARIANT=81) and prints, per key tile, when each warp role passed its wait points (cycles relative to the
+variant (B200_IMAGEN_FA_VARIANT=81: two issuer threads, 115: three) and prints, per key tile, when each warp role passed its wait points (cycles relative to the
 tile's first event).  Roles: warp 0 TMA producer, warps 1-2 MMA issuers of query tile A/B, warps 4-19 softmax (group = (w-4)//8)."""
 import os
 import struct

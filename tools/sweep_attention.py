@@ -5,9 +5,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = {-1: 'product path', 12: 'pp16 (r01 default)', 20: 'pt16', 41: 'pt16 nosub p1/8', 54: 'pt16 nosub wa p1/8', 60: 'pt16 wa pch p1/8', 59: 'pt16 pre p1/8',
-         65: 'pt16 pre p1/6', 66: 'pt16 pre', 71: 'pt16 pre late p1/8', 78: 'pt16 pre x64 p1/6', 82: 'pt16 pre order p1/6', 69: 'ABL pre no-MUFU',
-         110: 'split-S p1/6', 111: 'split-S p1/8', 112: 'split-S p1/4', 113: 'split-S', 114: 'ABL split-S no-MUFU', 116: 'split-S late p1/6', 117: 'split-S p1/3', 118: 'split-S late p1/4', 119: 'split-S late p1/3', 124: 'split-S p1/2', 120: 'persistent split-S p1/6', 121: 'persistent split-S p1/4', 122: 'persistent split-S p1/3', 123: 'ABL persistent split-S no-MUFU', 100: 'dual p1/6', 101: 'dual p1/8', 102: 'dual p1/4', 103: 'dual', 104: 'ABL dual no-MUFU', 90: 'persistent p1/6', 94: 'ABL persistent no-MUFU', 95: 'persistent rot p1/6'}
+NAMES = {-1: 'product path', 12: 'pp16 (r01 default)', 20: 'pt16', 41: 'pt16 nosub p1/8', 60: 'pt16 wa pch p1/8', 59: 'pt16 pre p1/8',
+         65: 'pt16 pre p1/6', 82: 'pt16 pre order p1/6', 112: 'split-S p1/4', 118: 'split-S late p1/4', 69: 'ABL pre no-MUFU', 114: 'ABL split-S no-MUFU',
+         100: 'dual p1/6', 104: 'ABL dual no-MUFU', 90: 'persistent p1/6', 121: 'persistent split-S p1/4', 123: 'ABL persistent split-S no-MUFU'}
 CODE = '''
 import sys, torch
 sys.path.insert(0, %r)
