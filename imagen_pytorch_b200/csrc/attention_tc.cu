@@ -552,15 +552,9 @@ flash_attn_pt_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < CH; ++i) sr[i] = __float_as_uint(-1.f - (float)(lane + i));
           } else {
-            if (CH == 64 && (MODE & 128)) {          // MODE bit 7: one x64 load instead of two x32 loads in flight
-              tmem_ld64_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0), sr);
-            } else {
+            // (one x64 load, or the two x32 loads one after the other, measured the same: profiles/r02_attention_preload_sweep.txt)
 #pragma unroll
-              for (int c = 0; c < CH; c += 32) {
-                tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
-                if ((MODE & 256) && c + 32 < CH) tmem_ld_wait();   // MODE bit 8: one load in flight at a time
-              }
-            }
+            for (int c = 0; c < CH; c += 32) tmem_ld32_nowait(tmem_base + lane_off + (uint32_t)(g * FA_BN + hf * 64 + c0 + c), sr + c);
             tmem_ld_wait();
           }
 #pragma unroll
@@ -1468,7 +1462,7 @@ int b200_attention_tc(const void* q, void* o, int64_t q_bs, int64_t q_hs, int32_
     B200_CUDA_OK(b200_launch(flash_attn_ptp_kernel<POLY, MODE>, dim3((unsigned)ctas), dim3(640), PT_SMEM, st, mq, mk, mv, p, pp));  \
   }
   // MODE bits of flash_attn_pt_kernel: 1 no "- C", 2/4 ablations, 8 warp-elected arrivals, 16 score preload, 32 chunked P hand-over,
-  // 64 late P-buffer wait, 128 x64 tcgen05.ld, 256 sequential loads, 512 time-line trace
+  // 64 late P-buffer wait, 512 time-line trace, 1024 S MMAs on a third issuer thread
   switch (variant) {
     case -1:                                     // product path
       if (persistent_on && ntiles <= FA_PERSISTENT_MAX_TILES) PTP_LAUNCH(4, 8)
