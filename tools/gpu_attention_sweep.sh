@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call L: attention barrier-chain experiments (one arrival per warp, P handed over in 32-key chunks, score preload)
+# attention variant sweep: attention barrier-chain experiments (one arrival per warp, P handed over in 32-key chunks, score preload)
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 OUT=gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call T: full GPU suite with the new attention defaults, full-length bench (both arms), ncu --set full of the attention kernels, launch list
+# full validation: full GPU suite with the new attention defaults, full-length bench (both arms), ncu --set full of the attention kernels, launch list
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 OUT=gpurun_out
