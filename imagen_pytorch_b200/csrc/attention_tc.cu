@@ -9,7 +9,7 @@
 // Kernels in this file (history and measurements: DESIGN.md section 3, profiles/r0*_attention_*):
 //   flash_attn_pp_kernel   ping-pong over two 128-row query tiles, P through shared memory (round-1 default, kept as variant 12)
 //   flash_attn_pt_kernel   + P in tensor memory (tcgen05.st, TS-form MMA), scores preloaded so that S is released before the first
-//                          exponential: the default for long key sequences (variant 65)
+//                          exponential, three elect.sync issuer threads: the default for long key sequences (variant 118)
 //   flash_attn_ptp_kernel  the same pipeline as persistent CTAs: the default for <= FA_PERSISTENT_MAX_TILES key tiles
 //   cross_attn_tc_kernel   <= 64 keys (cross-attention over the text tokens), persistent, K/V of all heads resident
 // Every kernel: warp 0 TMA producer (Q tiles, K/V ring, 128-byte swizzle), one MMA-issuer thread per query tile, softmax warps

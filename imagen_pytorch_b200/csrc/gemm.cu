@@ -1212,9 +1212,10 @@ conv_gemm_tcS_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------ tcgen05 kernel, transposed (<= 128 output channels)
-// For layers with <= 128 output channels the M128 x N128 MMA of the kernel above is the bottleneck: every K=16 instruction reads 4 KB of A
-// and 4 KB of B from shared memory for 64 cycles of math and the two do not overlap (878 TFLOP/s issue-only, vs 1398 for N = 256;
-// profiles/r01_gemm_bottleneck.txt), and per 128 x 128 tile the CTA pulls 32 KB of operands through L2 per 2.1 MFLOP.  This kernel computes
+// OPT-IN (B200_IMAGEN_GEMM_T=1).  Written when the 128 x 128-tile kernel above measured 878 TFLOP/s MMA-only against 1398 for 256-wide tiles
+// (profiles/r01_gemm_bottleneck.txt) -- attributed then to operand fetch, in fact the per-instruction ELECT loops of its issuer thread (see
+// elect_one in ptx.cuh): with those gone the row-major kernel reaches 1140 TFLOP/s MMA-only and wins (profiles/r02_gemm_after_elect.txt).
+// Per 128 x 128 tile the row-major CTA pulls 32 KB of operands through L2 per 2.1 MFLOP.  This kernel computes
 // the TRANSPOSED product  D^T[c][pixel] = sum_k W[c][k] * X[pixel][k]:  the weights are the M = 128 operand, a tile of 256 output pixels is the
 // N = 256 operand (same shared-memory layouts, roles swapped), i.e. the instruction shape and operand traffic of the 256-wide tiles.
 // The accumulator then holds channels in TMEM lanes and pixels in columns, so the epilogue transposes through shared memory:
