@@ -402,7 +402,7 @@ def main():
         line['roofline_conv'] = {'kernel': 'conv_gemm_tc_kernel<128,6,1,8,0> (tcgen05 implicit-GEMM conv3x3 128->128 @64x64, 128 x 128 tiles, MMAs issued under elect.sync)', 'bound': 'tensor',
                                  'achieved': conv_gflop / conv_ms, 'peak': pk['tensor_burst'], 'unit': 'TFLOP/s', 'frac': conv_gflop / conv_ms / pk['tensor_burst'],
                                  'traffic': 34.0e6, 'ms_per_launch': conv_ms, 'algorithmic_gflop_per_launch': conv_gflop,
-                                 'note': 'L2 flushed between launches; dram traffic from ncu = 33.9 MB read (input 33.5 MB read once), output stays in L2'}
+                                 'note': 'L2 flushed between launches; dram traffic from ncu --set full = 33.9 MB read + 1.4 MB written (profiles/r02_ncu_conv_gemm_summary.txt: input 33.5 MB read once, the 33.5 MB output stays in L2)'}
         step_tflop = GFLOP_PER_FORWARD_DIM128 * 2 * args.bs * args.timesteps / 1e3 if args.dim == 128 else None
         if step_tflop:
             ach = step_tflop / (ms / args.steps / 1e3)
