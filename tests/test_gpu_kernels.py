@@ -394,6 +394,22 @@ def test_cross_attention_tc_many_samples_per_cta(B, n, nk, heads):
     assert_close(o, ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('variant', [12, 60, 82, 90, 100])
+def test_attention_alternative_kernels_stay_correct(variant):
+    """The kept, selectable alternatives of the self-attention kernel (round-1 ping-pong kernel, chunked P hand-over, MUFU token, persistent at
+    any length, dual softmax) pass the same parity cases as the product path (child process: the variant is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('B200_IMAGEN_FA_VARIANT'):
+        pytest.skip('already inside a child')
+    env = dict(os.environ, B200_IMAGEN_FA_VARIANT=str(variant))
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-p', 'no:cacheprovider', __file__, '-m', 'gpu', '-k', 'test_multi_query_attention or test_cross_attention_layout_per_head_kv'],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout and 'no tests ran' not in r.stdout, r.stdout[-500:]
+
+
 # ------------------------------------------------------------------------------------------------ row-wise kernels
 
 @pytest.mark.parametrize('Cs,film', [([128], True), ([256, 128], False), ([1536, 768], True), ([32], False), ([40, 24], True)])
